@@ -1,0 +1,145 @@
+"""Generate the committed golden fixtures tests/golden/*.npz.
+
+Run HERE (the authoring container), where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Every expected value in the fixtures comes from the REFERENCE ITSELF:
+  * peaks      <- the reference's own Python NMS() (lib/utils/paf_to_pose.py:60-133) imported
+                  from /root/reference, run twice: with OpenCV's own bicubic code
+                  (cv2.ipp.setUseIPP(False); the bit-exact target) and with cv2's default IPP
+                  dispatch (the tolerance target, CPU-specific 1-ulp differences);
+  * subset / peak table / humans <- the UNMODIFIED reference C++ process_paf compiled into
+                  oracle/_ref/libpaf_ref.so, driven by the reference's paf_to_pose_cpp
+                  (paf_to_pose.py:346-380).
+The dense (north_star) front-end has no reference implementation; its expected peaks come from
+oracle/frontend_oracle.c (arithmetic defined there, "parity unpinned by the reference") and the
+people for those peaks again from the compiled reference process_paf.
+
+The reference cannot travel to the GPU box, the fixtures can.  Inputs are stored in the files,
+so nothing depends on NumPy's RNG stream staying stable.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import cv2  # noqa: E402
+
+import oracle  # noqa: E402
+from torch_ekpose_b200 import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def humans_to_array(humans):
+    """list[Human] -> (parts[n,18,4] = present,x,y,score ; scores[n])"""
+    parts = np.zeros((len(humans), 18, 4), np.float64)
+    scores = np.zeros(len(humans), np.float64)
+    for i, hm in enumerate(humans):
+        scores[i] = hm.score
+        for k, bp in hm.body_parts.items():
+            parts[i, k] = (1.0, bp.x, bp.y, bp.score)
+    return parts, scores
+
+
+def scene_fixture(name, heat, paf, p2p, cfg, ref, fe):
+    h, w = heat.shape[:2]
+    H, W = 8 * h, 8 * w
+    d = dict(heat=heat, paf=paf)
+
+    def ref_peaks():
+        jl = p2p.NMS(heat, upsampFactor=cfg.MODEL.DOWNSAMPLE, config=cfg)
+        rows = [tuple(pk) + (jt,) for jt, jp in enumerate(jl) for pk in jp]
+        return np.array(rows, np.float32).reshape(-1, 5)
+
+    cv2.ipp.setUseIPP(False)
+    d["ref_peaks"] = pk_off = ref_peaks()
+    humans_off = p2p.paf_to_pose_cpp(heat, paf, cfg)
+    d["ref_subset"] = ref.subset() if len(pk_off) else np.zeros((0, 20), np.float32)
+    x, y, s, i = ref.peaks_line() if len(pk_off) else [np.zeros(0)] * 4
+    d["ref_line_x"], d["ref_line_y"], d["ref_line_score"], d["ref_line_id"] = (
+        np.asarray(x, np.int32), np.asarray(y, np.int32), np.asarray(s, np.float32), np.asarray(i, np.int32))
+    d["ref_humans_parts"], d["ref_humans_score"] = humans_to_array(humans_off)
+
+    cv2.ipp.setUseIPP(True)
+    d["ref_peaks_ipp"] = pk_on = ref_peaks()
+    humans_on = p2p.paf_to_pose_cpp(heat, paf, cfg)
+    d["ref_subset_ipp"] = ref.subset() if len(pk_on) else np.zeros((0, 20), np.float32)
+    d["ref_humans_parts_ipp"], d["ref_humans_score_ipp"] = humans_to_array(humans_on)
+
+    # dense front-end: oracle-defined peaks, reference-computed people
+    S = fe.dense_smooth(heat)
+    d["dense_peaks"] = dpk = fe.dense_nms(S, np.float32(cfg.TEST.THRESH_HEATMAP))
+    paf_mat = fe.upsample_bilinear(paf)
+    sub, line = oracle.subset_of(ref, dpk, H, W, paf_mat)
+    d["dense_subset"] = sub
+    # a few probes of the smoothed / upsampled tensors (full tensors would be tens of MB)
+    rng = np.random.default_rng(12345)
+    ys = rng.integers(0, H, 64); xs = rng.integers(0, W, 64)
+    d["probe_yx"] = np.stack([ys, xs], 1).astype(np.int32)
+    d["probe_smooth"] = S[ys, xs, :]
+    d["probe_paf_mat"] = paf_mat[ys, xs, :]
+    d["probe_heat_mat"] = fe.upsample_bilinear(heat)[ys, xs, :]
+
+    same_xy = len(pk_off) == len(pk_on) and np.array_equal(pk_off[:, [0, 1, 3, 4]], pk_on[:, [0, 1, 3, 4]])
+    ties = 0
+    port = oracle.PortPaf()
+    if len(pk_off):
+        oracle.subset_of(port, pk_off, H, W, fe.upsample_nearest(paf))
+        for limb in range(19):
+            c = port.candidates(limb)["score"]
+            if len(c) > 16 and len(np.unique(c)) < len(c):
+                ties += 1
+    print(f"{name}: {h}x{w} peaks={len(pk_off)} humans={len(humans_off)} dense_peaks={len(dpk)} "
+          f"dense_humans={len(sub)} ipp_coords_same={same_xy} limbs_with_ties_over16={ties} "
+          f"humans_same_ipp={np.array_equal(d['ref_subset'][:, :18], d['ref_subset_ipp'][:, :18])}")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
+def kat_fixture(ref):
+    """SURVEY.md A.6 hand-checkable cases, answers from the compiled reference."""
+    d = {}
+    paf = np.zeros((64, 64, 38), np.float32)
+    paf[:, :, 12] = paf[:, :, 14] = paf[:, :, 16] = 1
+    chain = np.array([(10, 10, .9, 0, 1), (20, 10, .8, 1, 2), (30, 10, .7, 2, 3), (40, 10, .6, 3, 4)], np.float32)
+    cases = {
+        "chain": chain,
+        "chain_reversed": chain[::-1].copy(),           # A.1 quirk: ids follow input order
+        "short": chain[:3].copy(),                      # 3 parts -> pruned
+        "long_limb": np.array([(2, 2, .9, 0, 1), (62, 2, .8, 1, 2)], np.float32),  # norm > h1/2 -> penalty
+        "same_pixel": np.array([(10, 10, .9, 0, 1), (10, 10, .8, 1, 2)], np.float32),  # norm == 0 skipped
+    }
+    d["paf"] = paf
+    for k, pk in cases.items():
+        sub, line = oracle.subset_of(ref, pk, 64, 64, paf)
+        d[k + "_peaks"] = pk
+        d[k + "_subset"] = sub
+        d[k + "_line_x"] = line[0]
+        d[k + "_line_id"] = line[3]
+        print("kat", k, "humans", len(sub), sub[:, 18:] if len(sub) else "")
+    np.savez_compressed(os.path.join(OUT, "kat.npz"), **d)
+
+
+def main():
+    oracle.build(force=True)
+    p2p, cfg, ref = oracle.reference_python()
+    fe = oracle.Frontend()
+    scenes = {
+        "c1_46x54_p3": synthetic.make_scene(46, 54, 3, 1003),
+        "c2_46x54_p6": synthetic.make_scene(46, 54, 6, 2006),
+        "c3_46x82_p8": synthetic.make_scene(46, 82, 8, 3008),
+        "c4_crowd_64x96_p24": synthetic.make_scene(64, 96, 24, 4024),
+    }
+    empty_heat, empty_paf = synthetic.make_scene(46, 54, 0, 5000, noise=False)
+    scenes["empty_46x54"] = (empty_heat, empty_paf)
+    for name, (heat, paf) in scenes.items():
+        scene_fixture(name, heat, paf, p2p, cfg, ref, fe)
+    kat_fixture(ref)
+
+
+if __name__ == "__main__":
+    main()
