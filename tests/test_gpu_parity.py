@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): peak coordinates, peak counts, person count and part indices
+bit-exact; connection scores within 1e-5 relative -- the tests below demand BIT equality of the
+float32 scores as well, because scores decide sort order and ties.
+Only the reference front-end's peak SCORES carry a tolerance (2.5e-7 abs) when compared with cv2's
+default IPP build; against OpenCV's own code path they too are bit-exact.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+from tests.util import assert_bits_equal, golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ek():
+    import torch_ekpose_b200 as ek
+    return ek
+
+
+@pytest.fixture(scope="module")
+def pp(ek):
+    p = ek.PostProcessor(device=0, max_batch=64, max_h=92, max_w=164, max_peaks=2048, max_humans=128)
+    yield p
+    p.close()
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _nchw(hwc):
+    return np.ascontiguousarray(hwc.transpose(2, 0, 1))[None]
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference operator surface: process_paf / get_*  (stages 4-5 on host pointers)
+# ---------------------------------------------------------------------------------------------
+def _compat_subset(ek):
+    pf = ek.pafprocess
+    n = pf.get_num_humans()
+    cids = np.array([[pf.get_part_cid(h, p) for p in range(18)] for h in range(n)], np.int32).reshape(n, 18)
+    scores = np.array([pf.get_score(h) for h in range(n)], np.float32)
+    return n, cids, scores
+
+
+@pytest.mark.parametrize("case", ["chain", "chain_reversed", "short", "long_limb", "same_pixel"])
+def test_process_paf_known_answers(ek, case):
+    g = golden("kat")
+    pk, want = g[case + "_peaks"], g[case + "_subset"]
+    assert ek.pafprocess.process_paf(pk[None], np.zeros((64, 64, 19), np.float32), g["paf"]) == 0
+    n, cids, scores = _compat_subset(ek)
+    assert n == len(want)
+    if n:
+        assert np.array_equal(cids, want[:, :18].astype(np.int32))
+        assert_bits_equal(scores, want[:, 18] / want[:, 19], "human score")
+        # the A.1 quirk: get_part_x(cid) indexes the part-sorted table by input-order id
+        for cid in range(len(pk)):
+            assert ek.pafprocess.get_part_x(cid) == int(g[case + "_line_x"][cid])
+    if case == "chain":
+        assert n == 1 and float(scores[0]) == 1.5 and list(cids[0][1:5]) == [0, 1, 2, 3]
+
+
+@pytest.mark.parametrize("scene", util.SCENES)
+def test_process_paf_golden(ek, scene):
+    """Reference peaks + nearest-upsampled PAF in, the compiled reference's subset out (bit-exact)."""
+    g = golden(scene)
+    pk = g["ref_peaks"]
+    h, w = g["heat"].shape[:2]
+    paf_up = np.repeat(np.repeat(g["paf"], 8, axis=0), 8, axis=1)
+    if len(pk) == 0:
+        return  # the reference never calls process_paf without peaks (paf_to_pose.py:354)
+    assert ek.pafprocess.process_paf(pk[None], np.zeros((8 * h, 8 * w, 19), np.float32), paf_up) == 0
+    n, cids, scores = _compat_subset(ek)
+    want = g["ref_subset"]
+    assert n == len(want)
+    assert np.array_equal(cids, want[:, :18].astype(np.int32))
+    assert_bits_equal(scores, (want[:, 18] / want[:, 19]).astype(np.float32), "human score")
+    for cid in range(len(pk)):
+        assert ek.pafprocess.get_part_x(cid) == int(g["ref_line_x"][cid])
+        assert ek.pafprocess.get_part_y(cid) == int(g["ref_line_y"][cid])
+        assert np.float32(ek.pafprocess.get_part_score(cid)).view(np.uint32) == g["ref_line_score"][cid].view(np.uint32)
+
+
+def test_process_paf_rejects_bad_input(ek):
+    paf = np.zeros((16, 16, 38), np.float32)
+    bad_part = np.array([[(1, 1, .5, 0, 18)]], np.float32)
+    with pytest.raises(ValueError):
+        ek.pafprocess.process_paf(bad_part, np.zeros((16, 16, 19), np.float32), paf)
+    outside = np.array([[(99, 1, .5, 0, 1)]], np.float32)
+    with pytest.raises(ValueError):
+        ek.pafprocess.process_paf(outside, np.zeros((16, 16, 19), np.float32), paf)
+    with pytest.raises(TypeError):
+        ek.pafprocess.process_paf(np.zeros((2, 5), np.float32), np.zeros((16, 16, 19), np.float32), paf)
+    # zero peaks: zero humans, no error
+    assert ek.pafprocess.process_paf(np.zeros((1, 0, 5), np.float32), np.zeros((16, 16, 19), np.float32), paf) == 0
+    assert ek.pafprocess.get_num_humans() == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# reference front-end (stages 1-3 as the reference's Python does them) + stages 4-5
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("scene", util.SCENES)
+def test_reference_frontend_golden(pp, scene, layout):
+    g = golden(scene)
+    heat = _dev(_nchw(g["heat"]) if layout == "nchw" else g["heat"][None])
+    paf = _dev(_nchw(g["paf"]) if layout == "nchw" else g["paf"][None])
+    pp.run(heat, paf, layout=layout, frontend="reference")
+    res = pp.results(with_peaks=True)
+    got = util.peaks_table(res, 0)
+    want = g["ref_peaks"]           # reference NMS() with OpenCV's own bicubic code
+    assert got.shape == want.shape
+    assert np.array_equal(got[:, [0, 1, 3, 4]], want[:, [0, 1, 3, 4]])      # coords, ids, parts: exact
+    assert_bits_equal(got[:, 2], want[:, 2], "peak score vs cv2 (IPP off)")
+    want_ipp = g["ref_peaks_ipp"]   # cv2 default build (IPP): same coordinates, scores to 2.5e-7
+    assert np.array_equal(got[:, [0, 1, 3, 4]], want_ipp[:, [0, 1, 3, 4]])
+    if len(want_ipp):
+        assert np.abs(got[:, 2] - want_ipp[:, 2]).max() <= 2.5e-7
+    n = int(res["num_humans"][0])
+    assert n == len(g["ref_subset"])
+    assert_bits_equal(res["subset"][0, :n], g["ref_subset"], "subset")
+    # person count and part indices also equal the reference run with IPP on
+    assert np.array_equal(res["subset"][0, :n, :18], g["ref_subset_ipp"][:, :18])
+
+
+@pytest.mark.parametrize("scene", util.SCENES)
+def test_paf_to_pose_cpp_dropin(ek, scene):
+    """The reference-facing function: numpy HWC in, list[Human] out, equal to the reference's humans."""
+    g = golden(scene)
+    humans = ek.paf_to_pose_cpp(g["heat"], g["paf"], ek.cfg)
+    want_parts, want_score = g["ref_humans_parts"], g["ref_humans_score"]
+    assert len(humans) == len(want_score)
+    for k, hm in enumerate(humans):
+        assert hm.score == want_score[k]
+        present = {int(i) for i in np.nonzero(want_parts[k, :, 0])[0]}
+        assert set(hm.body_parts) == present
+        for part, bp in hm.body_parts.items():
+            assert bp.uidx == "%d-%d" % (k, part) and bp.part_idx == part
+            assert (bp.x, bp.y, bp.score) == tuple(want_parts[k, part, 1:])
+    # a transposed view of a CHW array (what estimator.get_outputs returns) takes the no-copy route
+    chw_h = np.ascontiguousarray(g["heat"].transpose(2, 0, 1))
+    chw_p = np.ascontiguousarray(g["paf"].transpose(2, 0, 1))
+    humans2 = ek.paf_to_pose_cpp(chw_h.transpose(1, 2, 0), chw_p.transpose(1, 2, 0), ek.cfg)
+    assert [sorted(h.body_parts) for h in humans2] == [sorted(h.body_parts) for h in humans]
+
+
+def test_nms_dropin(ek):
+    g = golden("c2_46x54_p6")
+    lists = ek.NMS(g["heat"], upsampFactor=8, config=ek.cfg)
+    flat = np.array([tuple(r) + (k,) for k, rows in enumerate(lists) for r in rows], np.float32)
+    assert_bits_equal(flat, g["ref_peaks"], "NMS joint list")
+
+
+# ---------------------------------------------------------------------------------------------
+# dense front-end (north_star stages 1-3) + stages 4-5
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("materialize", [True, False])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("scene", util.SCENES)
+def test_dense_frontend_golden(pp, scene, layout, materialize):
+    g = golden(scene)
+    heat = _dev(_nchw(g["heat"]) if layout == "nchw" else g["heat"][None])
+    paf = _dev(_nchw(g["paf"]) if layout == "nchw" else g["paf"][None])
+    pp.run(heat, paf, layout=layout, frontend="dense", materialize=materialize)
+    res = pp.results(with_peaks=True)
+    got = util.peaks_table(res, 0)
+    assert_bits_equal(got, g["dense_peaks"], "dense peaks")
+    n = int(res["num_humans"][0])
+    assert n == len(g["dense_subset"])
+    assert_bits_equal(res["subset"][0, :n], g["dense_subset"], "dense subset (people from the compiled reference)")
+    if materialize:
+        ys, xs = g["probe_yx"][:, 0], g["probe_yx"][:, 1]
+        assert_bits_equal(pp.paf_mat[0].cpu().numpy()[ys, xs], g["probe_paf_mat"], "paf_mat probes")
+        assert_bits_equal(pp.heat_mat[0].cpu().numpy()[ys, xs], g["probe_heat_mat"], "heat_mat probes")
+
+
+@pytest.mark.parametrize("shape", [(46, 54), (46, 82), (33, 40), (5, 5), (7, 70)])
+def test_dense_tensors_vs_oracle(pp, shape):
+    """Whole smoothed map and both operator-surface tensors, every element, against the oracle."""
+    from torch_ekpose_b200 import synthetic
+    h, w = shape
+    heat, paf = synthetic.make_scene(h, w, 3, 77 + h * w)
+    fe = util.frontend()
+    sm = pp.dense_smooth(_dev(_nchw(heat))).cpu().numpy()[0]
+    assert_bits_equal(sm, fe.dense_smooth(heat), "smoothed heat map")
+    pp.run(_dev(_nchw(heat)), _dev(_nchw(paf)), frontend="dense", materialize=True)
+    pp.results()
+    assert_bits_equal(pp.paf_mat[0].cpu().numpy(), fe.upsample_bilinear(paf), "paf_mat")
+    assert_bits_equal(pp.heat_mat[0].cpu().numpy(), fe.upsample_bilinear(heat), "heat_mat")
+
+
+def test_nearest_operator_surface(pp):
+    """REFERENCE front-end with materialisation: paf_mat / heat_mat == cv2 INTER_NEAREST x8."""
+    g = golden("c1_46x54_p3")
+    pp.run(_dev(_nchw(g["heat"])), _dev(_nchw(g["paf"])), frontend="reference", materialize=True)
+    pp.results()
+    assert np.array_equal(pp.paf_mat[0].cpu().numpy(), np.repeat(np.repeat(g["paf"], 8, 0), 8, 1))
+    assert np.array_equal(pp.heat_mat[0].cpu().numpy(), np.repeat(np.repeat(g["heat"], 8, 0), 8, 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configurations, batched, against the live oracle
+# ---------------------------------------------------------------------------------------------
+def _check_batch(pp, heat, paf, frontend, materialize, images):
+    pp.run(_dev(heat), _dev(paf), frontend=frontend, materialize=materialize)
+    res = pp.results(with_peaks=True)
+    assert not res["overflow"].any()
+    for i in images:
+        hw, pw = np.ascontiguousarray(heat[i].transpose(1, 2, 0)), np.ascontiguousarray(paf[i].transpose(1, 2, 0))
+        peaks, sub = (util.oracle_dense if frontend == "dense" else util.oracle_reference)(hw, pw)
+        assert_bits_equal(util.peaks_table(res, i), peaks, f"image {i} peaks")
+        n = int(res["num_humans"][i])
+        assert n == len(sub), f"image {i}: {n} humans vs {len(sub)}"
+        assert_bits_equal(res["subset"][i, :n], sub, f"image {i} subset")
+    return res
+
+
+@pytest.mark.parametrize("frontend,materialize", [("dense", True), ("dense", False), ("reference", False)])
+def test_config2_batch64_368x432(pp, frontend, materialize):
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(64, 46, 54, (1, 6), seed=2)
+    res = _check_batch(pp, heat, paf, frontend, materialize, range(0, 64, 3))
+    assert res["num_humans"].sum() > 150
+
+
+@pytest.mark.parametrize("frontend", ["dense", "reference"])
+def test_config3_656x368(pp, frontend):
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(32, 46, 82, (2, 8), seed=3)
+    _check_batch(pp, heat, paf, frontend, frontend == "dense", range(0, 32, 3))
+
+
+@pytest.mark.parametrize("frontend", ["dense", "reference"])
+def test_config4_crowded_1312x736(pp, frontend):
+    """30-40 people per image: >16 candidates per limb with exact score ties (std::sort emulation)."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(4, 92, 164, (30, 40), seed=4)
+    res = _check_batch(pp, heat, paf, frontend, False, range(4))
+    assert res["num_humans"].min() >= 25
+    ref = util.ref_or_none()
+    if ref is not None and frontend == "reference":   # and straight against the compiled reference
+        hw, pw = np.ascontiguousarray(heat[0].transpose(1, 2, 0)), np.ascontiguousarray(paf[0].transpose(1, 2, 0))
+        fe = util.frontend()
+        sub, _ = util.oracle_people(fe.ref_nms(hw), 736, 1312, fe.upsample_nearest(pw), impl=ref)
+        assert_bits_equal(res["subset"][0, :len(sub)], sub, "vs compiled reference")
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at full batch sizes
+# ---------------------------------------------------------------------------------------------
+def test_properties_batch_layout_materialise_invariance(pp):
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(64, 46, 54, (1, 6), seed=9)
+    hd, pd = _dev(heat), _dev(paf)
+
+    def run(hh, ppp, **kw):
+        pp.run(hh, ppp, **kw)
+        r = pp.results(with_peaks=True)
+        return r
+
+    a = run(hd, pd, frontend="dense", materialize=True)
+    b = run(hd, pd, frontend="dense", materialize=False)                     # lean == materialised
+    c = run(hd.permute(0, 2, 3, 1).contiguous(), pd.permute(0, 2, 3, 1).contiguous(), layout="nhwc", frontend="dense")
+    d = run(hd.flip(0).contiguous(), pd.flip(0).contiguous(), frontend="dense", materialize=True)  # batch order
+    e = run(hd, pd, frontend="dense", materialize=True)                      # determinism (atomics order)
+    for other, flip in ((b, False), (c, False), (d, True), (e, False)):
+        for k in ("num_humans", "n_peaks"):
+            assert np.array_equal(a[k], other[k][::-1] if flip else other[k])
+        sub = other["subset"][::-1] if flip else other["subset"]
+        pk = other["peaks"][::-1] if flip else other["peaks"]
+        for i in range(64):
+            n, m = int(a["num_humans"][i]), int(a["n_peaks"][i])
+            assert_bits_equal(a["subset"][i, :n], sub[i, :n])
+            assert np.array_equal(a["peaks"][i][:m], pk[i][:m])
+    # single-image runs equal the batched result
+    for i in (0, 17, 63):
+        s = run(hd[i:i + 1], pd[i:i + 1], frontend="dense")
+        n = int(a["num_humans"][i])
+        assert int(s["num_humans"][0]) == n
+        assert_bits_equal(s["subset"][0, :n], a["subset"][i, :n])
+
+
+def test_run_peaks_random_lists_vs_oracle(pp):
+    """Stage 4-5 device entry: unsorted peak lists with duplicates, random PAF."""
+    rng = np.random.default_rng(5)
+    n, H, W, stride = 6, 96, 128, 160
+    paf = rng.normal(0, 0.6, (n, H, W, 38)).astype(np.float32)
+    peaks = np.zeros((n, stride, 5), np.float32)
+    counts = np.array([0, 1, 40, 90, 160, 120], np.int32)
+    for i in range(n):
+        k = counts[i]
+        peaks[i, :k, 0] = rng.integers(0, W, k)
+        peaks[i, :k, 1] = rng.integers(0, H, k)
+        peaks[i, :k, 2] = rng.random(k)
+        peaks[i, :k, 4] = rng.integers(0, 18, k)
+        if k > 10:
+            peaks[i, 5:10, :2] = peaks[i, 0:5, :2]   # duplicate coordinates
+    pp.run_peaks(_dev(peaks), _dev(counts), _dev(paf), h1=H)
+    res = pp.results(with_peaks=True)
+    for i in range(n):
+        if counts[i] == 0:
+            assert res["num_humans"][i] == 0
+            continue
+        sub, line = util.oracle_people(peaks[i, :counts[i]], H, W, paf[i])
+        m = int(res["num_humans"][i])
+        assert m == len(sub)
+        assert_bits_equal(res["subset"][i, :m], sub, f"image {i}")
+        got = res["peaks"][i][:counts[i]]
+        assert np.array_equal(got["x"], line[0]) and np.array_equal(got["id"], line[3])
+
+
+# ---------------------------------------------------------------------------------------------
+# capacity and argument errors are reported, never silent
+# ---------------------------------------------------------------------------------------------
+def test_overflow_is_reported(ek):
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(2, 46, 54, (6, 6), seed=1)
+    small = ek.PostProcessor(device=0, max_batch=2, max_h=46, max_w=54, max_peaks=16, max_humans=2)
+    small.run(_dev(heat), _dev(paf), frontend="dense")
+    with pytest.raises(ek._lib.EkpCapacityError):
+        small.results()
+    small.close()
+
+
+def test_argument_errors(ek, pp):
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(1, 46, 54, (1, 1), seed=1)
+    with pytest.raises(ValueError):
+        pp.run(_dev(heat), _dev(paf[:, :37]), frontend="dense")
+    tiny = _dev(np.zeros((1, 19, 4, 4), np.float32)), _dev(np.zeros((1, 38, 4, 4), np.float32))
+    with pytest.raises(ek._lib.EkpError):
+        pp.run(*tiny, frontend="dense")
+    big = _dev(np.zeros((65, 19, 5, 5), np.float32)), _dev(np.zeros((65, 38, 5, 5), np.float32))
+    with pytest.raises(ek._lib.EkpError):
+        pp.run(*big, frontend="dense")

@@ -1,0 +1,560 @@
+// capi.cu -- the C ABI of libekpose_b200.so (include/ekpose_b200.h): context and work buffers,
+// the batched device API, and the reference's process_paf / get_* operator surface
+// (/root/reference/lib/pafprocess/pafprocess.h:53-59) on top of the same kernels.
+// Host code only orchestrates: every stage of the path runs in the CUDA kernels of this
+// directory and there is no CPU implementation to fall back to.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ekp {
+// kernels (one translation unit each)
+size_t dense_frontend_smem_bytes(int tile_wl);
+int dense_frontend_tile_wl(int w);
+cudaError_t configure_dense_frontend();
+cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream);
+cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream);
+cudaError_t launch_upsample_nearest(const float* lo, int layout, int n, int h, int w, int C, float* out, cudaStream_t stream);
+cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fixed, int peaks_stride, int p3, int n, int W,
+                                int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow, cudaStream_t stream);
+cudaError_t configure_peaks_sort(int raw_cap);
+cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int id_from_key, int n, ekp_peak* line,
+                              int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
+cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int max_peaks, const PafSource& paf, int h1, int n,
+                               Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream);
+cudaError_t configure_assemble(int max_humans);
+cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const Conn* conns, const int* n_conns, int max_humans, int n,
+                            float* subset_out, int* num_humans, ekp_peak* hparts, float* hscore, unsigned* overflow,
+                            cudaStream_t stream);
+}  // namespace ekp
+
+using namespace ekp;
+
+// ---- error reporting -------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(expr)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) return fail(EKP_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* ekp_last_error(void) { return g_err; }
+extern "C" const char* ekp_version(void) { return "ekpose_b200 0.1 (sm_100a)"; }
+
+// ---- host-side tables --------------------------------------------------------------------------
+// Composite operator  A = Gaussian(sigma 3, radius 12, scipy 'reflect')  x  bilinear x8 (half-pixel,
+// clamp) for an axis with n stride-8 samples, as 5 taps on stride-8 samples starting at
+// clamp(D/8 - 2, 0, n-5).  Built in double and rounded once, in the accumulation order the
+// oracle defines (oracle/frontend_oracle.c okp_dense_tables), padded to 8 floats per row.
+static int reflect_idx(int i, int n) {
+    while (i < 0 || i >= n) { if (i < 0) i = -i - 1; if (i >= n) i = 2 * n - 1 - i; }
+    return i;
+}
+static int build_dense_taps(int n, std::vector<float>& taps) {
+    const int N = 8 * n;
+    if (n < 5) return -1;
+    double wd[25], sum = 0.0;
+    for (int j = -12; j <= 12; j++) { wd[j + 12] = exp(-0.5 * (double) (j * j) / 9.0); sum += wd[j + 12]; }
+    for (int j = 0; j < 25; j++) wd[j] /= sum;
+    taps.assign((size_t) N * 8, 0.f);
+    std::vector<double> row(n);
+    for (int D = 0; D < N; D++) {
+        for (int i = 0; i < n; i++) row[i] = 0.0;
+        for (int j = -12; j <= 12; j++) {
+            const int Dp = reflect_idx(D + j, N);
+            int i0 = (Dp + 4) / 8 - 1;
+            const double t = (double) (2 * ((Dp + 4) % 8) + 1) / 16.0;
+            const int i1 = i0 + 1 > n - 1 ? n - 1 : i0 + 1;
+            if (i0 < 0) i0 = 0;
+            row[i0] += wd[j + 12] * (1.0 - t);
+            row[i1] += wd[j + 12] * t;
+        }
+        int base = D / 8 - 2;
+        if (base < 0) base = 0;
+        if (base > n - 5) base = n - 5;
+        for (int i = 0; i < n; i++)
+            if (row[i] != 0.0 && (i < base || i >= base + 5)) return -2;  // support must fit the window
+        for (int k = 0; k < 5; k++) taps[(size_t) D * 8 + k] = (float) row[base + k];
+    }
+    return 0;
+}
+// cv2 interpolateCubic (A = -0.75) in float arithmetic for t = (2k+1)/16; volatile keeps the host
+// compiler from contracting or reassociating.
+static void build_cubic_table(float* tab /* [8][4] */) {
+    for (int k = 0; k < 8; k++) {
+        volatile float x = (float) (2 * k + 1) / 16.0f;
+        const float A = -0.75f;
+        volatile float x1 = x + 1, xm = 1 - x;
+        volatile float c0 = A * x1; c0 = c0 - 5 * A; c0 = c0 * x1; c0 = c0 + 8 * A; c0 = c0 * x1; c0 = c0 - 4 * A;
+        volatile float c1 = (A + 2) * x; c1 = c1 - (A + 3); c1 = c1 * x; c1 = c1 * x; c1 = c1 + 1;
+        volatile float c2 = (A + 2) * xm; c2 = c2 - (A + 3); c2 = c2 * xm; c2 = c2 * xm; c2 = c2 + 1;
+        volatile float c3 = 1.f - c0; c3 = c3 - c1; c3 = c3 - c2;
+        tab[k * 4 + 0] = c0; tab[k * 4 + 1] = c1; tab[k * 4 + 2] = c2; tab[k * 4 + 3] = c3;
+    }
+}
+
+// ---- context -----------------------------------------------------------------------------------
+struct ekp_ctx {
+    int device = 0, max_batch = 0, max_h = 0, max_w = 0, max_peaks = 0, max_humans = 0;
+    // device work buffers
+    RawPeak* raw = nullptr;
+    int* raw_count = nullptr;       // [max_batch]
+    unsigned* overflow = nullptr;   // [max_batch]  (contiguous with raw_count: one memset)
+    ekp_peak* line = nullptr;       // [max_batch][max_peaks]
+    int* part_off = nullptr;        // [max_batch][20]
+    int* n_peaks = nullptr;         // [max_batch]
+    Conn* conns = nullptr;          // [max_batch][19][EKP_MAX_PART]
+    int* n_conns = nullptr;         // [max_batch][19]
+    float* subset = nullptr;        // [max_batch][max_humans][20]
+    int* num_humans = nullptr;      // [max_batch]
+    ekp_peak* hparts = nullptr;     // [max_batch][max_humans][18]
+    float* hscore = nullptr;        // [max_batch][max_humans]
+    float* in_heat = nullptr;       // staging for the host-buffer entry points
+    float* in_paf = nullptr;
+    float* mat_heat = nullptr;      // context-owned operator-surface tensors (host entry, lazily)
+    float* mat_paf = nullptr;
+    size_t mat_images = 0, mat_hw = 0;
+    float* ax = nullptr;            // dense taps for (tab_h, tab_w)
+    float* ay = nullptr;
+    int tab_h = 0, tab_w = 0;
+    float* cubic = nullptr;         // [8][4]
+    // pinned host mirrors of the results
+    int* h_num_humans = nullptr;
+    int* h_n_peaks = nullptr;
+    unsigned* h_overflow = nullptr;
+    float* h_subset = nullptr;
+    ekp_peak* h_hparts = nullptr;
+    float* h_hscore = nullptr;
+    ekp_peak* h_line = nullptr;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    int last_n = 0;
+    bool has_run = false;
+    long long launches = 0;
+    // optional per-stage timing: events recorded on the work stream around each stage
+    static const int kRing = 64;
+    bool timing = false;
+    cudaEvent_t tev[kRing][5] = {};
+    long long timed_runs = 0;
+};
+
+static inline void mark(ekp_ctx* c, int k, cudaStream_t st) {
+    if (c->timing) cudaEventRecord(c->tev[c->timed_runs % ekp_ctx::kRing][k], st);
+}
+
+static int ctx_free(ekp_ctx* c) {
+    if (!c) return EKP_OK;
+    cudaSetDevice(c->device);
+    void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->subset, c->num_humans,
+                   c->hparts, c->hscore, c->in_heat, c->in_paf, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {c->h_num_humans, c->h_n_peaks, c->h_overflow, c->h_subset, c->h_hparts, c->h_hscore, c->h_line};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    if (c->done) cudaEventDestroy(c->done);
+    for (auto& row : c->tev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
+    delete c;
+    return EKP_OK;
+}
+
+extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, int max_w, int max_peaks, int max_humans) {
+    if (!out) return fail(EKP_ERR_ARG, "ekp_create: out is NULL");
+    *out = nullptr;
+    if (max_batch < 1 || max_h < 5 || max_w < 5 || max_peaks < 1 || max_humans < 1 || max_peaks > 16384 || max_humans > 2048)
+        return fail(EKP_ERR_ARG, "ekp_create: bad capacity (batch %d, map %dx%d >= 5x5, peaks %d <= 16384, humans %d <= 2048)",
+                    max_batch, max_h, max_w, max_peaks, max_humans);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(EKP_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(EKP_ERR_ARG, "ekp_create: device %d of %d", device, ndev);
+    CU(cudaSetDevice(device));
+    ekp_ctx* c = new ekp_ctx();
+    c->device = device; c->max_batch = max_batch; c->max_h = max_h; c->max_w = max_w;
+    c->max_peaks = max_peaks; c->max_humans = max_humans;
+    const size_t B = (size_t) max_batch;
+#define DEV_ALLOC(ptr, bytes)                                                     \
+    do {                                                                          \
+        cudaError_t _e = cudaMalloc((void**) &(ptr), (bytes));                    \
+        if (_e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "cudaMalloc(%zu) for " #ptr ": %s", (size_t) (bytes), cudaGetErrorString(_e)); } \
+    } while (0)
+#define HOST_ALLOC(ptr, bytes)                                                    \
+    do {                                                                          \
+        cudaError_t _e = cudaMallocHost((void**) &(ptr), (bytes));                \
+        if (_e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "cudaMallocHost(%zu) for " #ptr ": %s", (size_t) (bytes), cudaGetErrorString(_e)); } \
+    } while (0)
+    DEV_ALLOC(c->raw, sizeof(RawPeak) * B * max_peaks);
+    DEV_ALLOC(c->raw_count, sizeof(int) * 2 * B);
+    c->overflow = reinterpret_cast<unsigned*>(c->raw_count + B);
+    DEV_ALLOC(c->line, sizeof(ekp_peak) * B * max_peaks);
+    DEV_ALLOC(c->part_off, sizeof(int) * B * 20);
+    DEV_ALLOC(c->n_peaks, sizeof(int) * B);
+    DEV_ALLOC(c->conns, sizeof(Conn) * B * EKP_NUM_LIMB * EKP_MAX_PART);
+    DEV_ALLOC(c->n_conns, sizeof(int) * B * EKP_NUM_LIMB);
+    DEV_ALLOC(c->subset, sizeof(float) * B * max_humans * 20);
+    DEV_ALLOC(c->num_humans, sizeof(int) * B);
+    DEV_ALLOC(c->hparts, sizeof(ekp_peak) * B * max_humans * EKP_NUM_PART);
+    DEV_ALLOC(c->hscore, sizeof(float) * B * max_humans);
+    DEV_ALLOC(c->cubic, sizeof(float) * 32);
+    HOST_ALLOC(c->h_num_humans, sizeof(int) * B);
+    HOST_ALLOC(c->h_n_peaks, sizeof(int) * B);
+    HOST_ALLOC(c->h_overflow, sizeof(unsigned) * B);
+    HOST_ALLOC(c->h_subset, sizeof(float) * B * max_humans * 20);
+    HOST_ALLOC(c->h_hparts, sizeof(ekp_peak) * B * max_humans * EKP_NUM_PART);
+    HOST_ALLOC(c->h_hscore, sizeof(float) * B * max_humans);
+    HOST_ALLOC(c->h_line, sizeof(ekp_peak) * B * max_peaks);
+    float cubic[32];
+    build_cubic_table(cubic);
+    e = cudaMemcpy(c->cubic, cubic, sizeof(cubic), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = configure_dense_frontend();
+    if (e == cudaSuccess) e = configure_peaks_sort(max_peaks);
+    if (e == cudaSuccess) e = configure_assemble(max_humans);
+    if (e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "context setup: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return EKP_OK;
+}
+
+extern "C" void ekp_destroy(ekp_ctx* ctx) { ctx_free(ctx); }
+extern "C" int ekp_max_batch(const ekp_ctx* c) { return c ? c->max_batch : 0; }
+extern "C" int ekp_max_peaks(const ekp_ctx* c) { return c ? c->max_peaks : 0; }
+extern "C" int ekp_max_humans(const ekp_ctx* c) { return c ? c->max_humans : 0; }
+extern "C" long long ekp_kernel_launches(const ekp_ctx* c) { return c ? c->launches : 0; }
+
+static int ensure_tables(ekp_ctx* c, int h, int w, cudaStream_t stream) {
+    if (c->tab_h == h && c->tab_w == w) return EKP_OK;
+    std::vector<float> tx, ty;
+    if (build_dense_taps(w, tx) || build_dense_taps(h, ty)) return fail(EKP_ERR_ARG, "dense front-end needs h, w >= 5 (got %dx%d)", h, w);
+    CU(cudaStreamSynchronize(stream));  // nothing in flight may still read the old tables
+    if (c->ax) { cudaFree(c->ax); c->ax = nullptr; }
+    if (c->ay) { cudaFree(c->ay); c->ay = nullptr; }
+    c->tab_h = c->tab_w = 0;
+    CU(cudaMalloc((void**) &c->ax, tx.size() * sizeof(float)));
+    CU(cudaMalloc((void**) &c->ay, ty.size() * sizeof(float)));
+    CU(cudaMemcpy(c->ax, tx.data(), tx.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->ay, ty.data(), ty.size() * sizeof(float), cudaMemcpyHostToDevice));
+    c->tab_h = h; c->tab_w = w;
+    return EKP_OK;
+}
+
+static int check_shape(const ekp_ctx* c, int n, int h, int w, int layout, const char* who) {
+    if (!c) return fail(EKP_ERR_ARG, "%s: NULL context", who);
+    if (n < 1 || n > c->max_batch) return fail(EKP_ERR_ARG, "%s: batch %d outside [1, %d]", who, n, c->max_batch);
+    if (h < 5 || w < 5 || h > c->max_h || w > c->max_w)
+        return fail(EKP_ERR_ARG, "%s: stride-8 map %dx%d outside [5x5, %dx%d]", who, h, w, c->max_h, c->max_w);
+    if (8 * h > 65535 || 8 * w > 65535) return fail(EKP_ERR_ARG, "%s: full-resolution map larger than 65535", who);
+    if (layout != EKP_LAYOUT_NCHW && layout != EKP_LAYOUT_NHWC) return fail(EKP_ERR_ARG, "%s: layout %d", who, layout);
+    return EKP_OK;
+}
+
+// stages 4-5 + result copies, shared by every entry point
+static int run_back_half(ekp_ctx* c, int n, int id_from_key, const PafSource& paf, int h1, cudaStream_t st) {
+    mark(c, 1, st);
+    CU(launch_peaks_sort(c->raw, c->raw_count, c->max_peaks, id_from_key, n, c->line, c->part_off, c->n_peaks, c->overflow, st));
+    mark(c, 2, st);
+    CU(launch_paf_connect(c->line, c->part_off, c->max_peaks, paf, h1, n, c->conns, c->n_conns, c->overflow, st));
+    mark(c, 3, st);
+    CU(launch_assemble(c->line, c->max_peaks, c->conns, c->n_conns, c->max_humans, n, c->subset, c->num_humans, c->hparts,
+                       c->hscore, c->overflow, st));
+    mark(c, 4, st);
+    if (c->timing) c->timed_runs++;
+    c->launches += 3;
+    CU(cudaMemcpyAsync(c->h_num_humans, c->num_humans, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_n_peaks, c->n_peaks, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_overflow, c->overflow, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_subset, c->subset, sizeof(float) * 20 * (size_t) n * c->max_humans, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_hparts, c->hparts, sizeof(ekp_peak) * EKP_NUM_PART * (size_t) n * c->max_humans, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_hscore, c->hscore, sizeof(float) * (size_t) n * c->max_humans, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->done, st));
+    c->last_stream = st; c->last_n = n; c->has_run = true;
+    return EKP_OK;
+}
+
+extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, int n, int h, int w, int layout,
+                               float thr_heat, int frontend, float* heat_mat, float* paf_mat, void* stream) {
+    int rc = check_shape(c, n, h, w, layout, "ekp_postprocess");
+    if (rc) return rc;
+    if (!heat || !paf) return fail(EKP_ERR_ARG, "ekp_postprocess: NULL input");
+    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE) return fail(EKP_ERR_ARG, "ekp_postprocess: frontend %d", frontend);
+    if (heat_mat && !paf_mat) return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat without paf_mat");
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+    PafSource src;
+    src.layout = layout; src.H = 8 * h; src.W = 8 * w; src.C = EKP_PAF_CH; src.h = h; src.w = w;
+    if (frontend == EKP_FRONTEND_DENSE) {
+        rc = ensure_tables(c, h, w, st);
+        if (rc) return rc;
+        mark(c, 0, st);
+        DenseParams p;
+        p.heat = heat; p.paf = paf; p.n = n; p.h = h; p.w = w; p.layout = layout; p.thr = thr_heat;
+        p.ax = c->ax; p.ay = c->ay; p.heat_mat = heat_mat; p.paf_mat = paf_mat; p.smooth_out = nullptr;
+        p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.tile_wl = dense_frontend_tile_wl(w);
+        CU(launch_dense_frontend(p, st));
+        c->launches += 1;
+        if (paf_mat) { src.ptr = paf_mat; src.mode = PAF_FULL_HWC; }
+        else { src.ptr = paf; src.mode = PAF_LO_BILINEAR; }
+    } else {
+        mark(c, 0, st);
+        RefParams p;
+        p.heat = heat; p.n = n; p.h = h; p.w = w; p.layout = layout; p.thr = thr_heat;
+        p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.cubic = c->cubic;
+        CU(launch_ref_frontend(p, st));
+        c->launches += 1;
+        if (paf_mat) { CU(launch_upsample_nearest(paf, layout, n, h, w, EKP_PAF_CH, paf_mat, st)); c->launches += 1; }
+        if (heat_mat) { CU(launch_upsample_nearest(heat, layout, n, h, w, EKP_HEAT_CH, heat_mat, st)); c->launches += 1; }
+        src.ptr = paf; src.mode = PAF_LO_NEAREST;  // == paf_mat[y][x] exactly (cv2 INTER_NEAREST x8)
+    }
+    return run_back_half(c, n, /*id_from_key=*/0, src, /*h1=*/8 * h, st);
+}
+
+extern "C" int ekp_postprocess_host(ekp_ctx* c, const float* heat_host, const float* paf_host, int n, int h, int w,
+                                    int layout, float thr_heat, int frontend, int materialize, void* stream) {
+    int rc = check_shape(c, n, h, w, layout, "ekp_postprocess_host");
+    if (rc) return rc;
+    if (!heat_host || !paf_host) return fail(EKP_ERR_ARG, "ekp_postprocess_host: NULL input");
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(c->device));
+    if (!c->in_heat) {
+        CU(cudaMalloc((void**) &c->in_heat, sizeof(float) * (size_t) c->max_batch * c->max_h * c->max_w * EKP_HEAT_CH));
+        CU(cudaMalloc((void**) &c->in_paf, sizeof(float) * (size_t) c->max_batch * c->max_h * c->max_w * EKP_PAF_CH));
+    }
+    const size_t hw = (size_t) h * w;
+    float *hm = nullptr, *pm = nullptr;
+    if (materialize) {
+        if (c->mat_images < (size_t) n || c->mat_hw < hw) {
+            CU(cudaStreamSynchronize(st));
+            if (c->mat_heat) { cudaFree(c->mat_heat); c->mat_heat = nullptr; }
+            if (c->mat_paf) { cudaFree(c->mat_paf); c->mat_paf = nullptr; }
+            c->mat_images = 0; c->mat_hw = 0;
+            const size_t ni = (size_t) n;
+            CU(cudaMalloc((void**) &c->mat_heat, sizeof(float) * ni * hw * 64 * EKP_HEAT_CH));
+            CU(cudaMalloc((void**) &c->mat_paf, sizeof(float) * ni * hw * 64 * EKP_PAF_CH));
+            c->mat_images = ni; c->mat_hw = hw;
+        }
+        hm = c->mat_heat; pm = c->mat_paf;
+    }
+    CU(cudaMemcpyAsync(c->in_heat, heat_host, sizeof(float) * (size_t) n * hw * EKP_HEAT_CH, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->in_paf, paf_host, sizeof(float) * (size_t) n * hw * EKP_PAF_CH, cudaMemcpyHostToDevice, st));
+    return ekp_postprocess(c, c->in_heat, c->in_paf, n, h, w, layout, thr_heat, frontend, hm, pm, stream);
+}
+
+extern "C" int ekp_process_paf_dev(ekp_ctx* c, const float* peaks, const int* n_peaks, int peaks_stride, int n, int h1,
+                                   const float* paf_mat, int H, int W, int C, void* stream) {
+    if (!c) return fail(EKP_ERR_ARG, "ekp_process_paf_dev: NULL context");
+    if (n < 1 || n > c->max_batch) return fail(EKP_ERR_ARG, "ekp_process_paf_dev: batch %d outside [1, %d]", n, c->max_batch);
+    if (!peaks || !paf_mat || !n_peaks) return fail(EKP_ERR_ARG, "ekp_process_paf_dev: NULL input");
+    if (H < 1 || W < 1 || C < 38 || peaks_stride < 1) return fail(EKP_ERR_ARG, "ekp_process_paf_dev: bad dims H=%d W=%d C=%d (C >= 38)", H, W, C);
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+    mark(c, 0, st);
+    CU(launch_peaks_ingest(peaks, n_peaks, 0, peaks_stride, 5, n, W, H, c->raw, c->raw_count, c->max_peaks, c->overflow, st));
+    c->launches += 1;
+    PafSource src;
+    src.ptr = paf_mat; src.mode = PAF_FULL_HWC; src.layout = EKP_LAYOUT_NHWC; src.H = H; src.W = W; src.C = C; src.h = H / 8; src.w = W / 8;
+    return run_back_half(c, n, /*id_from_key=*/1, src, h1, st);
+}
+
+static int wait_results(ekp_ctx* c, const char* who) {
+    if (!c) return fail(EKP_ERR_ARG, "%s: NULL context", who);
+    if (!c->has_run) return fail(EKP_ERR_STATE, "%s: no run has been submitted on this context", who);
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->done));
+    return EKP_OK;
+}
+static int overflow_status(const ekp_ctx* c) {
+    unsigned any = 0;
+    for (int i = 0; i < c->last_n; i++) any |= c->h_overflow[i];
+    if (any & EKP_OVF_BADPEAK) return fail(EKP_ERR_ARG, "a peak has part id outside [0,18), coordinates outside the PAF map, or a NaN score");
+    if (any) return fail(EKP_ERR_CAPACITY, "capacity overflow (bits 0x%x: 1 peaks>%d, 2 part>%d, 4 candidates>%d, 8 humans>%d)", any,
+                         c->max_peaks, EKP_MAX_PART, EKP_MAX_CAND, c->max_humans);
+    return EKP_OK;
+}
+
+extern "C" int ekp_results(ekp_ctx* c, int* num_humans, float* subset, int* n_peaks, ekp_peak* peaks_line, unsigned* overflow) {
+    int rc = wait_results(c, "ekp_results");
+    if (rc) return rc;
+    const int n = c->last_n;
+    if (num_humans) memcpy(num_humans, c->h_num_humans, sizeof(int) * n);
+    if (n_peaks) memcpy(n_peaks, c->h_n_peaks, sizeof(int) * n);
+    if (overflow) memcpy(overflow, c->h_overflow, sizeof(unsigned) * n);
+    if (subset) memcpy(subset, c->h_subset, sizeof(float) * 20 * (size_t) n * c->max_humans);
+    if (peaks_line) {  // the big table is only fetched on request
+        CU(cudaMemcpyAsync(c->h_line, c->line, sizeof(ekp_peak) * (size_t) n * c->max_peaks, cudaMemcpyDeviceToHost, c->last_stream));
+        CU(cudaStreamSynchronize(c->last_stream));
+        memcpy(peaks_line, c->h_line, sizeof(ekp_peak) * (size_t) n * c->max_peaks);
+    }
+    return overflow_status(c);
+}
+
+extern "C" int ekp_results_humans(ekp_ctx* c, int* num_humans, ekp_peak* parts, float* scores, unsigned* overflow) {
+    int rc = wait_results(c, "ekp_results_humans");
+    if (rc) return rc;
+    const int n = c->last_n;
+    if (num_humans) memcpy(num_humans, c->h_num_humans, sizeof(int) * n);
+    if (overflow) memcpy(overflow, c->h_overflow, sizeof(unsigned) * n);
+    if (parts) memcpy(parts, c->h_hparts, sizeof(ekp_peak) * EKP_NUM_PART * (size_t) n * c->max_humans);
+    if (scores) memcpy(scores, c->h_hscore, sizeof(float) * (size_t) n * c->max_humans);
+    return overflow_status(c);
+}
+
+extern "C" int ekp_set_timing(ekp_ctx* c, int enable) {
+    if (!c) return fail(EKP_ERR_ARG, "ekp_set_timing: NULL context");
+    CU(cudaSetDevice(c->device));
+    if (enable && !c->tev[0][0])
+        for (auto& row : c->tev) for (cudaEvent_t& e : row) CU(cudaEventCreate(&e));
+    c->timing = enable != 0;
+    c->timed_runs = 0;
+    return EKP_OK;
+}
+
+extern "C" int ekp_stage_times(ekp_ctx* c, float* ms, int* runs) {
+    int rc = wait_results(c, "ekp_stage_times");
+    if (rc) return rc;
+    if (!ms) return fail(EKP_ERR_ARG, "ekp_stage_times: NULL pointer");
+    CU(cudaStreamSynchronize(c->last_stream));
+    const long long have = c->timed_runs < ekp_ctx::kRing ? c->timed_runs : ekp_ctx::kRing;
+    double acc[4] = {0, 0, 0, 0};
+    for (long long r = 0; r < have; r++)
+        for (int k = 0; k < 4; k++) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, c->tev[r][k], c->tev[r][k + 1]));
+            acc[k] += t;
+        }
+    for (int k = 0; k < 4; k++) ms[k] = have ? (float) (acc[k] / (double) have) : 0.f;
+    if (runs) *runs = (int) have;
+    return EKP_OK;
+}
+
+extern "C" int ekp_results_parts(ekp_ctx* c, int* part_off) {
+    int rc = wait_results(c, "ekp_results_parts");
+    if (rc) return rc;
+    if (!part_off) return fail(EKP_ERR_ARG, "ekp_results_parts: NULL pointer");
+    std::vector<int> tmp((size_t) c->last_n * 20);
+    CU(cudaMemcpyAsync(tmp.data(), c->part_off, sizeof(int) * tmp.size(), cudaMemcpyDeviceToHost, c->last_stream));
+    CU(cudaStreamSynchronize(c->last_stream));
+    for (int i = 0; i < c->last_n; i++) memcpy(part_off + (size_t) i * 19, tmp.data() + (size_t) i * 20, sizeof(int) * 19);
+    return EKP_OK;
+}
+
+extern "C" int ekp_dense_smooth_debug(ekp_ctx* c, const float* heat, int n, int h, int w, int layout, float* smooth_out, void* stream) {
+    int rc = check_shape(c, n, h, w, layout, "ekp_dense_smooth_debug");
+    if (rc) return rc;
+    if (!heat || !smooth_out) return fail(EKP_ERR_ARG, "ekp_dense_smooth_debug: NULL pointer");
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(c->device));
+    rc = ensure_tables(c, h, w, st);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+    DenseParams p;
+    p.heat = heat; p.paf = nullptr; p.n = n; p.h = h; p.w = w; p.layout = layout; p.thr = INFINITY;
+    p.ax = c->ax; p.ay = c->ay; p.heat_mat = nullptr; p.paf_mat = nullptr; p.smooth_out = smooth_out;
+    p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.tile_wl = dense_frontend_tile_wl(w);
+    CU(launch_dense_frontend(p, st));
+    c->launches += 1;
+    return EKP_OK;
+}
+
+// ---- the reference operator surface ------------------------------------------------------------
+// Process-global "last result", like the reference's globals (pafprocess.cpp:12-13).
+namespace {
+std::mutex g_mu;
+ekp_ctx* g_ctx = nullptr;
+float* g_dev_peaks = nullptr; size_t g_dev_peaks_cap = 0;
+float* g_dev_paf = nullptr; size_t g_dev_paf_cap = 0;
+std::vector<float> g_subset;      // [num_humans][20]
+std::vector<float> g_hscore;      // [num_humans] subset[18] / subset[19], computed on the device
+std::vector<ekp_peak> g_line;     // part-sorted peak table
+int g_num_humans = 0;
+
+int compat_ctx(int need_peaks, int need_humans) {
+    if (g_ctx && g_ctx->max_peaks >= need_peaks && g_ctx->max_humans >= need_humans) return EKP_OK;
+    int dev = 0;
+    if (const char* s = getenv("EKP_DEVICE")) dev = atoi(s);
+    int peaks = 1024, humans = 128;
+    while (peaks < need_peaks) peaks *= 2;
+    while (humans < need_humans) humans *= 2;
+    if (g_ctx) { ekp_destroy(g_ctx); g_ctx = nullptr; }
+    return ekp_create(&g_ctx, dev, 1, 8, 8, peaks, humans);
+}
+}  // namespace
+
+extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, float* heatmap, int f1, int f2,
+                           int f3, float* pafmap) {
+    (void) h2; (void) h3; (void) heatmap;  // heat_mat is used only through h1 (pafprocess.cpp:83)
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_num_humans = 0; g_subset.clear(); g_hscore.clear(); g_line.clear();
+    if (p1 < 0 || p2 < 0 || p3 < 5 || f1 < 1 || f2 < 1 || f3 < 38 || !pafmap || (!peaks && (long long) p1 * p2 > 0))
+        return fail(EKP_ERR_ARG, "process_paf: bad arguments (peaks [%d,%d,%d] needs p3 >= 5, paf [%d,%d,%d] needs f3 >= 38)", p1, p2, p3, f1, f2, f3);
+    const long long npk = (long long) p1 * p2;  // all p1 "images" are pooled (pafprocess.cpp:26-36)
+    if (npk > 16384) return fail(EKP_ERR_CAPACITY, "process_paf: %lld peaks > 16384", npk);
+    if (npk == 0) return EKP_OK;  // nothing to connect: zero humans, like the reference
+    int need_humans = 128;
+    for (int attempt = 0; attempt < 5; attempt++) {
+        int rc = compat_ctx((int) npk, need_humans);
+        if (rc) return rc;
+        ekp_ctx* c = g_ctx;
+        CU(cudaSetDevice(c->device));
+        const size_t pk_elems = (size_t) npk * p3, paf_elems = (size_t) f1 * f2 * f3;
+        if (g_dev_peaks_cap < pk_elems) { if (g_dev_peaks) cudaFree(g_dev_peaks); g_dev_peaks = nullptr; g_dev_peaks_cap = 0;
+            CU(cudaMalloc((void**) &g_dev_peaks, pk_elems * sizeof(float))); g_dev_peaks_cap = pk_elems; }
+        if (g_dev_paf_cap < paf_elems) { if (g_dev_paf) cudaFree(g_dev_paf); g_dev_paf = nullptr; g_dev_paf_cap = 0;
+            CU(cudaMalloc((void**) &g_dev_paf, paf_elems * sizeof(float))); g_dev_paf_cap = paf_elems; }
+        cudaStream_t st = nullptr;
+        const int npk_i = (int) npk;
+        CU(cudaMemcpyAsync(g_dev_peaks, peaks, pk_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(g_dev_paf, pafmap, paf_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+        mark(c, 0, st);
+        CU(launch_peaks_ingest(g_dev_peaks, nullptr, npk_i, npk_i, p3, 1, f2, f1, c->raw, c->raw_count, c->max_peaks, c->overflow, st));
+        c->launches += 1;
+        PafSource src;
+        src.ptr = g_dev_paf; src.mode = PAF_FULL_HWC; src.layout = EKP_LAYOUT_NHWC; src.H = f1; src.W = f2; src.C = f3; src.h = f1 / 8; src.w = f2 / 8;
+        rc = run_back_half(c, 1, /*id_from_key=*/1, src, h1, st);
+        if (rc) return rc;
+        std::vector<ekp_peak> line((size_t) c->max_peaks);
+        std::vector<float> subset((size_t) c->max_humans * 20);
+        int nh = 0, np = 0;
+        unsigned ovf = 0;
+        rc = ekp_results(c, &nh, subset.data(), &np, line.data(), &ovf);
+        if (rc == EKP_ERR_CAPACITY && ovf == EKP_OVF_HUMANS && need_humans < 2048) { need_humans *= 4; continue; }
+        if (rc) return rc;
+        g_num_humans = nh;
+        g_subset.assign(subset.begin(), subset.begin() + (size_t) nh * 20);
+        g_hscore.assign(c->h_hscore, c->h_hscore + nh);
+        g_line.assign(line.begin(), line.begin() + np);
+        return EKP_OK;  // the reference returns 0 (pafprocess.cpp:193)
+    }
+    return fail(EKP_ERR_CAPACITY, "process_paf: more than 2048 subset rows");
+}
+
+extern "C" int get_num_humans(void) { return g_num_humans; }
+extern "C" int get_part_cid(int human_id, int part_id) {
+    if (human_id < 0 || human_id >= g_num_humans || part_id < 0 || part_id >= EKP_SUBSET_COLS) { fail(EKP_ERR_ARG, "get_part_cid(%d, %d) out of range", human_id, part_id); return -1; }
+    return (int) g_subset[(size_t) human_id * 20 + part_id];
+}
+extern "C" float get_score(int human_id) {
+    if (human_id < 0 || human_id >= g_num_humans) { fail(EKP_ERR_ARG, "get_score(%d) out of range", human_id); return 0.f; }
+    return g_hscore[(size_t) human_id];
+}
+static const ekp_peak* peak_at(int cid, const char* who) {
+    if (cid < 0 || (size_t) cid >= g_line.size()) { fail(EKP_ERR_ARG, "%s(%d) out of range", who, cid); return nullptr; }
+    return &g_line[(size_t) cid];
+}
+extern "C" int get_part_x(int cid) { const ekp_peak* p = peak_at(cid, "get_part_x"); return p ? p->x : 0; }
+extern "C" int get_part_y(int cid) { const ekp_peak* p = peak_at(cid, "get_part_y"); return p ? p->y : 0; }
+extern "C" float get_part_score(int cid) { const ekp_peak* p = peak_at(cid, "get_part_score"); return p ? p->score : 0.f; }

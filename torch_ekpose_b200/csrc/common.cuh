@@ -1,0 +1,96 @@
+// common.cuh -- shared device-side types for libekpose_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ekpose_b200.h"
+
+namespace ekp {
+
+// Unordered peak record produced by stages 1-3 (or by the peak-list ingest of process_paf).
+// Ordering is restored by peaks_sort_kernel from (part, key): the reference emits peaks in
+// (part, y, x) order (paf_to_pose.py:36, :350-352) and process_paf buckets by part keeping input
+// order (pafprocess.cpp:24-43).
+struct RawPeak {
+    int x;          // full-resolution column
+    int y;          // full-resolution row
+    float score;
+    int part;       // 0..17
+    unsigned key;   // order within the part: (row << 16 | col) of the maximum, or the input index
+};
+
+struct Conn {        // pafprocess.h:45-51
+    int cid1, cid2;
+    float score;
+    int pad;
+};
+
+// how stage 4 obtains paf_mat[y][x][ch]
+enum PafMode {
+    PAF_FULL_HWC = 0,      // gather from a materialised full-resolution [H][W][C] tensor
+    PAF_LO_NEAREST = 1,    // paf_lo[y>>3][x>>3]   (== cv2 INTER_NEAREST x8, paf_to_pose.py:356-357)
+    PAF_LO_BILINEAR = 2    // bilinear x8 of paf_lo, same arithmetic as the materialising kernel
+};
+
+struct PafSource {
+    const float* ptr;  // full-res HWC tensor, or stride-8 tensor
+    int mode;
+    int layout;        // of the stride-8 tensor (EKP_LAYOUT_*)
+    int H, W, C;       // full-resolution dims and channel count
+    int h, w;          // stride-8 dims (modes 1, 2)
+};
+
+// pafprocess.h:16-24
+__constant__ const int kPairsNet[EKP_NUM_LIMB][2] = {
+    {12, 13}, {20, 21}, {14, 15}, {16, 17}, {22, 23}, {24, 25}, {0, 1},   {2, 3},   {4, 5},   {6, 7},
+    {8, 9},   {10, 11}, {28, 29}, {30, 31}, {34, 35}, {32, 33}, {36, 37}, {18, 19}, {26, 27}};
+__constant__ const int kPairs[EKP_NUM_LIMB][2] = {
+    {1, 2},   {1, 5},   {2, 3},  {3, 4},   {5, 6},   {6, 7},  {1, 8},   {8, 9},  {9, 10}, {1, 11},
+    {11, 12}, {12, 13}, {1, 0},  {0, 14},  {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17}};
+
+// bilinear x8 with half-pixel centres: source index pair and weight for full-res coordinate D.
+// s = (D + 0.5)/8 - 0.5;  i0 = floor(s) = (D+4)/8 - 1;  t = s - i0 = (2*((D+4)%8) + 1)/16 (exact).
+__device__ __forceinline__ void bilin_coord(int D, int n, int& i0, int& i1, float& t) {
+    const int q = D + 4;
+    i0 = (q >> 3) - 1;
+    t = (float) (2 * (q & 7) + 1) * 0.0625f;
+    i1 = min(i0 + 1, n - 1);
+    i0 = max(i0, 0);
+}
+// a + t*(b - a) with one rounding in the subtract and one in the fused multiply-add; the CPU
+// oracle uses fmaf() for the same expression.
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return fmaf(t, __fsub_rn(b, a), a); }
+
+__device__ __forceinline__ float lo_at(const float* lo, int layout, int img, int C, int h, int w, int c, int j, int i) {
+    return layout == EKP_LAYOUT_NCHW ? __ldg(lo + (((size_t) img * C + c) * h + j) * w + i)
+                                     : __ldg(lo + (((size_t) img * h + j) * w + i) * C + c);
+}
+
+// launch parameter blocks --------------------------------------------------------------------
+struct DenseParams {
+    const float* heat;
+    const float* paf;
+    int n, h, w, layout;
+    float thr;
+    const float* ax;   // [8w][8] polyphase taps along x (5 used)
+    const float* ay;   // [8h][8] along y
+    float* heat_mat;   // nullable
+    float* paf_mat;    // nullable
+    float* smooth_out; // nullable debug output [n][8h][8w][18]
+    RawPeak* raw;
+    int* raw_count;
+    int raw_cap;
+    int tile_wl;       // stride-8 columns per tile
+};
+
+struct RefParams {
+    const float* heat;
+    int n, h, w, layout;
+    float thr;
+    RawPeak* raw;
+    int* raw_count;
+    int raw_cap;
+    const float* cubic; // [8][4] cv2 bicubic coefficients for t = (2k+1)/16
+};
+
+}  // namespace ekp

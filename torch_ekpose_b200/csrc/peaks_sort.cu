@@ -1,0 +1,109 @@
+// peaks_sort.cu -- peak ingest: from an unordered per-image peak list to the reference's
+// part-sorted peak table (`peak_infos_line`, pafprocess.cpp:24-43) and per-part offsets.
+//
+//   peaks_ingest_kernel : process_paf's own input format, float [p2][p3] rows
+//                         (x, y, score, _, part) -> RawPeak with key = input index
+//                         (pafprocess.cpp:26-36: x,y truncated to int, id = running input index).
+//   peaks_sort_kernel   : rank every peak by (part, key) -- unique keys, so the rank is a
+//                         permutation and the result is independent of the order in which the
+//                         front-end's atomics appended the peaks -- and scatter it to its row.
+//                         id = rank for the front-ends (their input order IS the sorted order,
+//                         paf_to_pose.py:350-352) or = input index for process_paf input, which
+//                         reproduces the reference's indexing of peak_infos_line by id
+//                         (pafprocess.cpp:208-218) including for unsorted input.
+#include "common.cuh"
+
+namespace ekp {
+
+__global__ void peaks_ingest_kernel(const float* __restrict__ peaks, const int* __restrict__ n_peaks, int n_fixed,
+                                    int peaks_stride, int p3, int W, int H, RawPeak* __restrict__ raw,
+                                    int* __restrict__ raw_count, int raw_cap, unsigned* __restrict__ overflow) {
+    const int img = blockIdx.y;
+    const int n = n_peaks ? n_peaks[img] : n_fixed;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) raw_count[img] = n;  // peaks_sort clamps to raw_cap and flags the overflow
+    if (k >= n || k >= raw_cap) return;
+    const float* row = peaks + ((size_t) img * peaks_stride + k) * p3;
+    RawPeak pk;
+    pk.x = (int) row[0];  // C truncation, pafprocess.cpp:30-31
+    pk.y = (int) row[1];
+    pk.score = row[2];
+    pk.part = (int) row[4];
+    pk.key = (unsigned) k;
+    if (pk.part < 0 || pk.part >= EKP_NUM_PART || pk.x < 0 || pk.x >= W || pk.y < 0 || pk.y >= H || !(pk.score == pk.score)) {
+        atomicOr(overflow + img, EKP_OVF_BADPEAK);  // the reference has undefined behaviour here; we refuse
+        pk.part = EKP_NUM_PART;                      // sorted behind every real part, never used
+        pk.x = pk.y = 0;
+    }
+    raw[(size_t) img * raw_cap + k] = pk;
+}
+
+// One block per image.  Dynamic shared memory: raw_cap 64-bit keys.
+__global__ void __launch_bounds__(256) peaks_sort_kernel(const RawPeak* __restrict__ raw, const int* __restrict__ raw_count,
+                                                         int raw_cap, int id_from_key, ekp_peak* __restrict__ line,
+                                                         int* __restrict__ part_off /* [n][20] */, int* __restrict__ n_peaks,
+                                                         unsigned* __restrict__ overflow) {
+    extern __shared__ unsigned long long sKey[];
+    __shared__ int sCount[EKP_NUM_PART + 1];
+    const int img = blockIdx.x;
+    const int total = raw_count[img];
+    const int n = min(total, raw_cap);
+    const RawPeak* r = raw + (size_t) img * raw_cap;
+    if (threadIdx.x <= EKP_NUM_PART) sCount[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        sKey[i] = ((unsigned long long) (unsigned) r[i].part << 32) | r[i].key;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = sKey[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const unsigned long long kj = sKey[j];
+            rank += (kj < k) || (kj == k && j < i);
+        }
+        const RawPeak pk = r[i];
+        ekp_peak out;
+        out.x = pk.x; out.y = pk.y; out.score = pk.score;
+        out.id = id_from_key ? (int) pk.key : rank;
+        line[(size_t) img * raw_cap + rank] = out;
+        atomicAdd(&sCount[min(pk.part, EKP_NUM_PART)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ovf = 0;
+        if (total > raw_cap) ovf |= EKP_OVF_PEAKS;
+        int off = 0;
+        int* po = part_off + (size_t) img * 20;
+        for (int p = 0; p < EKP_NUM_PART; p++) {
+            po[p] = off;
+            if (sCount[p] > EKP_MAX_PART) ovf |= EKP_OVF_PART;
+            off += sCount[p];
+        }
+        po[EKP_NUM_PART] = off;   // == number of valid peaks (invalid ones sort behind)
+        po[EKP_NUM_PART + 1] = n;
+        n_peaks[img] = off;
+        if (ovf) atomicOr(overflow + img, ovf);
+    }
+}
+
+cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fixed, int peaks_stride, int p3, int n,
+                                int W, int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow,
+                                cudaStream_t stream) {
+    const int maxn = min(peaks_stride, raw_cap);
+    dim3 grid((maxn + 127) / 128 > 0 ? (maxn + 127) / 128 : 1, n);
+    peaks_ingest_kernel<<<grid, 128, 0, stream>>>(peaks, n_peaks, n_fixed, peaks_stride, p3, W, H, raw, raw_count, raw_cap, overflow);
+    return cudaGetLastError();
+}
+
+cudaError_t configure_peaks_sort(int raw_cap) {
+    return cudaFuncSetAttribute(peaks_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) (sizeof(unsigned long long) * (size_t) raw_cap));
+}
+
+cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int id_from_key, int n, ekp_peak* line,
+                              int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream) {
+    const size_t smem = sizeof(unsigned long long) * (size_t) raw_cap;
+    peaks_sort_kernel<<<n, 256, smem, stream>>>(raw, raw_count, raw_cap, id_from_key, line, part_off, n_peaks, overflow);
+    return cudaGetLastError();
+}
+
+}  // namespace ekp

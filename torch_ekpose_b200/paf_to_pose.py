@@ -1,0 +1,314 @@
+"""Host side of the post-processing path: the reference's ``paf_to_pose`` interface on top of
+libekpose_b200.so.
+
+Mirrors /root/reference/lib/utils/paf_to_pose.py for the functions the inference scripts call
+(run_image.py:59, run_video.py:61, run_webcam.py:47, eval.py:156):
+
+* ``paf_to_pose_cpp(heatmaps, pafs, config)`` (:346-380)  numpy HWC in, ``list[Human]`` out;
+* ``NMS(heatmaps, upsampFactor, ..., config)``  (:60-133)  list of 18 ``[n_k, 4]`` arrays;
+
+and adds the batched entry points the B200 path is built around:
+
+* ``PostProcessor``      one context (= one GPU, one stream of work) with fixed-capacity buffers;
+* ``postprocess_batch``  heat / PAF tensors of a whole batch (CUDA tensors as the network emits
+                         them, or host arrays) -> per-image ``list[Human]``.
+
+Everything numerical happens in the CUDA library; this module converts arguments and builds
+``Human`` / ``BodyPart`` objects from the result tables.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .common import BodyPart, Human
+from .config import cfg as default_cfg
+
+try:  # torch is plumbing here (device memory and streams), not a requirement of the host path
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_PEAK_DT = np.dtype([("x", np.int32), ("y", np.int32), ("score", np.float32), ("id", np.int32)])
+_FRONTENDS = {"dense": _lib.FRONTEND_DENSE, "reference": _lib.FRONTEND_REFERENCE}
+_LAYOUTS = {"nchw": _lib.LAYOUT_NCHW, "nhwc": _lib.LAYOUT_NHWC}
+
+
+def _is_tensor(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class PostProcessor:
+    """A libekpose_b200 context: stages 1-5 for batches of up to ``max_batch`` images.
+
+    ``run`` is asynchronous on the current CUDA stream of ``device``; ``results`` / ``humans`` /
+    ``peaks`` wait for it.  Inputs are float32 stride-8 maps, ``heat`` with 19 and ``paf`` with 38
+    channels, layout ``'nchw'`` (lib/network/vgg2016.py:105) or ``'nhwc'``
+    (lib/evaluate/estimator.py:85-86).
+    """
+
+    def __init__(self, device: int = 0, max_batch: int = 64, max_h: int = 46, max_w: int = 54, max_peaks: int = 1024,
+                 max_humans: int = 64):
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        _lib.check(_lib.lib.ekp_create(C.byref(self._ctx), self.device, max_batch, max_h, max_w, max_peaks, max_humans))
+        self.max_batch, self.max_h, self.max_w = max_batch, max_h, max_w
+        self.max_peaks, self.max_humans = max_peaks, max_humans
+        self._keep = None      # inputs of the in-flight run
+        self._n = 0
+        self._hw = (0, 0)
+        self.heat_mat = None   # operator-surface tensors of the last materialising device run
+        self.paf_mat = None
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            _lib.lib.ekp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self, stream) -> int:
+        if stream is not None:
+            return int(getattr(stream, "cuda_stream", stream))
+        if torch is not None and torch.cuda.is_available():
+            return int(torch.cuda.current_stream(self.device).cuda_stream)
+        return 0
+
+    def _dims(self, heat_shape, paf_shape, layout):
+        if len(heat_shape) != 4 or len(paf_shape) != 4:
+            raise ValueError(f"heat / paf must be 4-D, got {tuple(heat_shape)} / {tuple(paf_shape)}")
+        if layout == "nchw":
+            n, ch, h, w = heat_shape
+            pn, pc, ph, pw = paf_shape
+        elif layout == "nhwc":
+            n, h, w, ch = heat_shape
+            pn, ph, pw, pc = paf_shape
+        else:
+            raise ValueError("layout must be 'nchw' or 'nhwc'")
+        if ch != _lib.HEAT_CH or pc != _lib.PAF_CH or (pn, ph, pw) != (n, h, w):
+            raise ValueError(f"expected heat with 19 and paf with 38 channels of equal batch/size, got "
+                             f"{tuple(heat_shape)} / {tuple(paf_shape)} ({layout})")
+        return int(n), int(h), int(w)
+
+    def run(self, heat, paf, *, layout: str = "nchw", frontend: str = "dense", thr: float = 0.15,
+            materialize: bool = False, stream=None) -> None:
+        """Submit one batch (n <= max_batch).  CUDA tensors take the device entry point; NumPy
+        arrays / CPU tensors take the host entry point (H2D copies on the same stream)."""
+        if frontend not in _FRONTENDS:
+            raise ValueError("frontend must be 'dense' or 'reference'")
+        n, h, w = self._dims(heat.shape, paf.shape, layout)
+        st = self._stream(stream)
+        thr = float(np.float32(thr))
+        if _is_tensor(heat) and heat.is_cuda:
+            if not (_is_tensor(paf) and paf.is_cuda and paf.device == heat.device):
+                raise ValueError("heat and paf must live on the same device")
+            if heat.device.index != self.device:
+                raise ValueError(f"tensors are on cuda:{heat.device.index}, context on cuda:{self.device}")
+            heat = heat.contiguous().float()
+            paf = paf.contiguous().float()
+            hm = pm = None
+            if materialize:
+                H, W = 8 * h, 8 * w
+                if self.paf_mat is None or self.paf_mat.shape != (n, H, W, _lib.PAF_CH):
+                    self.heat_mat = torch.empty((n, H, W, _lib.HEAT_CH), dtype=torch.float32, device=heat.device)
+                    self.paf_mat = torch.empty((n, H, W, _lib.PAF_CH), dtype=torch.float32, device=heat.device)
+                hm, pm = self.heat_mat.data_ptr(), self.paf_mat.data_ptr()
+            rc = _lib.lib.ekp_postprocess(self._ctx, heat.data_ptr(), paf.data_ptr(), n, h, w, _LAYOUTS[layout], thr,
+                                          _FRONTENDS[frontend], hm, pm, st)
+            self._keep = (heat, paf)
+        else:
+            if _is_tensor(heat):
+                heat_p, paf_p = heat.contiguous().float(), paf.contiguous().float()
+                ptrs = (heat_p.data_ptr(), paf_p.data_ptr())
+            else:
+                heat_p = np.ascontiguousarray(heat, np.float32)
+                paf_p = np.ascontiguousarray(paf, np.float32)
+                ptrs = (heat_p.ctypes.data, paf_p.ctypes.data)
+            rc = _lib.lib.ekp_postprocess_host(self._ctx, ptrs[0], ptrs[1], n, h, w, _LAYOUTS[layout], thr,
+                                               _FRONTENDS[frontend], int(bool(materialize)), st)
+            self._keep = (heat_p, paf_p)
+        _lib.check(rc)
+        self._n, self._hw = n, (h, w)
+
+    def run_peaks(self, peaks, n_peaks, paf_mat, h1: int, stream=None) -> None:
+        """Stages 4-5 only on DEVICE tensors: peaks float32 [n, stride, 5], n_peaks int32 [n],
+        paf_mat float32 [n, H, W, C] (the reference's process_paf arguments, batched)."""
+        n, stride, five = peaks.shape
+        if five != 5 or paf_mat.dim() != 4 or paf_mat.shape[0] != n:
+            raise ValueError("peaks must be [n, stride, 5] and paf_mat [n, H, W, C]")
+        peaks, paf_mat = peaks.contiguous().float(), paf_mat.contiguous().float()
+        n_peaks = n_peaks.contiguous().to(torch.int32)
+        _, H, W, Cc = paf_mat.shape
+        _lib.check(_lib.lib.ekp_process_paf_dev(self._ctx, peaks.data_ptr(), n_peaks.data_ptr(), stride, n, int(h1),
+                                                paf_mat.data_ptr(), H, W, Cc, self._stream(stream)))
+        self._keep = (peaks, n_peaks, paf_mat)
+        self._n, self._hw = n, (H // 8, W // 8)
+
+    # ------------------------------------------------------------------------------------------
+    def results(self, with_peaks: bool = False) -> dict:
+        """Wait and return numpy tables: num_humans [n], subset [n, max_humans, 20] (float32, the
+        reference's rows), n_peaks [n], overflow [n] and optionally peaks [n, max_peaks]
+        (structured x, y, score, id) + part_off [n, 19]."""
+        n = self._n
+        num = np.zeros(n, np.int32)
+        npk = np.zeros(n, np.int32)
+        ovf = np.zeros(n, np.uint32)
+        subset = np.zeros((n, self.max_humans, 20), np.float32)
+        line = np.zeros((n, self.max_peaks), _PEAK_DT) if with_peaks else None
+        rc = _lib.lib.ekp_results(self._ctx, num.ctypes.data, subset.ctypes.data, npk.ctypes.data,
+                                  line.ctypes.data if with_peaks else None, ovf.ctypes.data)
+        _lib.check(rc)
+        out = dict(num_humans=num, subset=subset, n_peaks=npk, overflow=ovf)
+        if with_peaks:
+            po = np.zeros((n, 19), np.int32)
+            _lib.check(_lib.lib.ekp_results_parts(self._ctx, po.ctypes.data))
+            out["peaks"] = line
+            out["part_off"] = po
+        return out
+
+    def human_tables(self):
+        """(num_humans [n], parts [n, max_humans, 18] structured (x, y, score, id; id -1 = absent),
+        scores [n, max_humans]) -- the whole getter loop of paf_to_pose_cpp in three arrays."""
+        n = self._n
+        num = np.zeros(n, np.int32)
+        parts = np.zeros((n, self.max_humans, _lib.NUM_PART), _PEAK_DT)
+        scores = np.zeros((n, self.max_humans), np.float32)
+        _lib.check(_lib.lib.ekp_results_humans(self._ctx, num.ctypes.data, parts.ctypes.data, scores.ctypes.data, None))
+        return num, parts, scores
+
+    def humans(self) -> List[List[Human]]:
+        """Per image the list[Human] the reference builds at paf_to_pose.py:361-378."""
+        num, parts, scores = self.human_tables()
+        h, w = self._hw
+        H, W = 8 * h, 8 * w
+        out = []
+        for i in range(self._n):
+            humans = []
+            for k in range(int(num[i])):
+                human = Human([])
+                row = parts[i, k]
+                for part_idx in np.nonzero(row["id"] >= 0)[0]:
+                    p = row[part_idx]
+                    human.body_parts[int(part_idx)] = BodyPart("%d-%d" % (k, part_idx), int(part_idx),
+                                                               float(p["x"]) / W, float(p["y"]) / H, float(p["score"]))
+                if human.body_parts:
+                    human.score = float(scores[i, k])
+                    humans.append(human)
+            out.append(humans)
+        return out
+
+    def set_timing(self, enable: bool) -> None:
+        _lib.check(_lib.lib.ekp_set_timing(self._ctx, int(bool(enable))))
+
+    def stage_times(self):
+        """Mean device milliseconds per stage over the recorded runs: dict + number of runs."""
+        ms = (C.c_float * 4)()
+        runs = C.c_int(0)
+        _lib.check(_lib.lib.ekp_stage_times(self._ctx, ms, C.byref(runs)))
+        return dict(frontend=ms[0], peak_sort=ms[1], connect=ms[2], assemble=ms[3]), runs.value
+
+    def kernel_launches(self) -> int:
+        return int(_lib.lib.ekp_kernel_launches(self._ctx))
+
+    def dense_smooth(self, heat, layout: str = "nchw"):
+        """Test hook: the dense front-end's smoothed map, CUDA tensor [n, 8h, 8w, 18]."""
+        if layout == "nchw":
+            n, _, h, w = heat.shape
+        else:
+            n, h, w, _ = heat.shape
+        heat = heat.contiguous().float()
+        out = torch.empty((n, 8 * h, 8 * w, _lib.NUM_PART), dtype=torch.float32, device=heat.device)
+        _lib.check(_lib.lib.ekp_dense_smooth_debug(self._ctx, heat.data_ptr(), n, h, w, _LAYOUTS[layout], out.data_ptr(),
+                                                   self._stream(None)))
+        return out
+
+
+# ---- module-level convenience API ---------------------------------------------------------------
+_cache: dict = {}
+
+
+def _processor(device: int, n: int, h: int, w: int, max_peaks: int, max_humans: int) -> PostProcessor:
+    key = (device,)
+    pp = _cache.get(key)
+    if pp is None or pp.max_batch < n or pp.max_h < h or pp.max_w < w or pp.max_peaks < max_peaks or pp.max_humans < max_humans:
+        if pp is not None:
+            pp.close()
+            max_peaks, max_humans = max(max_peaks, pp.max_peaks), max(max_humans, pp.max_humans)
+            n, h, w = max(n, pp.max_batch), max(h, pp.max_h), max(w, pp.max_w)
+        pp = _cache[key] = PostProcessor(device, n, h, w, max_peaks, max_humans)
+    return pp
+
+
+def postprocess_batch(heat, paf, *, layout: str = "nchw", frontend: str = "dense", thr: float = 0.15,
+                      materialize: bool = False, max_peaks: int = 2048, max_humans: int = 128,
+                      device: Optional[int] = None) -> List[List[Human]]:
+    """heat [n,19,h,w] / paf [n,38,h,w] (or NHWC) -> per-image list[Human].  CUDA tensors stay on
+    the device; host arrays are copied in.  On a capacity overflow the buffers are grown once."""
+    if device is None:
+        device = heat.device.index if (_is_tensor(heat) and heat.is_cuda) else 0
+    shp = heat.shape
+    n, h, w = (shp[0], shp[2], shp[3]) if layout == "nchw" else (shp[0], shp[1], shp[2])
+    for _ in range(3):
+        pp = _processor(device, int(n), int(h), int(w), max_peaks, max_humans)
+        pp.run(heat, paf, layout=layout, frontend=frontend, thr=thr, materialize=materialize)
+        try:
+            return pp.humans()
+        except _lib.EkpCapacityError:
+            max_peaks, max_humans = pp.max_peaks * 4, min(pp.max_humans * 4, 2048)
+    raise _lib.EkpCapacityError(_lib.ERR_CAPACITY, "result does not fit even after growing the buffers")
+
+
+def paf_to_pose_cpp(heatmaps, pafs, config=None, *, frontend: str = "reference") -> List[Human]:
+    """Drop-in for paf_to_pose.py:346-380: one image, numpy HWC ``heatmaps[h,w,19]``,
+    ``pafs[h,w,38]`` (the arrays estimator.get_outputs returns) -> ``list[Human]``.
+
+    The default front-end is the reference's own (stride-8 NMS + bicubic refinement), so the
+    people equal the reference's; ``frontend='dense'`` selects the north_star formulation.
+    Transposed views of NCHW arrays (what get_outputs actually returns, estimator.py:85-86) are
+    passed through without a host-side copy.
+    """
+    config = config or default_cfg
+    if config.MODEL.NUM_KEYPOINTS != 18 or config.MODEL.DOWNSAMPLE != 8:
+        raise ValueError("the CUDA path is built for NUM_KEYPOINTS=18, DOWNSAMPLE=8 (lib/config/default.py:16-17)")
+    heatmaps = np.asarray(heatmaps)
+    pafs = np.asarray(pafs)
+    if heatmaps.ndim != 3 or pafs.ndim != 3:
+        raise ValueError("heatmaps / pafs must be [h, w, C]")
+    layout = "nhwc"
+    hv, pv = heatmaps.transpose(2, 0, 1), pafs.transpose(2, 0, 1)
+    if hv.flags.c_contiguous and pv.flags.c_contiguous and heatmaps.dtype == np.float32 and pafs.dtype == np.float32:
+        heat4, paf4, layout = hv[None], pv[None], "nchw"   # a view of the network's CHW output: no copy
+    else:
+        heat4, paf4 = heatmaps[None], pafs[None]
+    return postprocess_batch(heat4, paf4, layout=layout, frontend=frontend, thr=config.TEST.THRESH_HEATMAP)[0]
+
+
+def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False, config=None):
+    """Drop-in for paf_to_pose.py:60-133: list of 18 float64 arrays ``[n_k, 4]`` = (x, y, score, id)."""
+    config = config or default_cfg
+    if not bool_refine_center or bool_gaussian_filt or int(upsampFactor) != 8:
+        raise NotImplementedError("only the configuration the reference's callers use is built: "
+                                  "upsampFactor=8, bool_refine_center=True, bool_gaussian_filt=False "
+                                  "(paf_to_pose.py:348)")
+    heatmaps = np.ascontiguousarray(heatmaps, np.float32)
+    h, w, _ = heatmaps.shape
+    pp = _processor(0, 1, h, w, 2048, 128)
+    pp.run(heatmaps[None], np.zeros((1, h, w, _lib.PAF_CH), np.float32), layout="nhwc", frontend="reference",
+           thr=config.TEST.THRESH_HEATMAP)
+    res = pp.results(with_peaks=True)
+    line, po = res["peaks"][0], res["part_off"][0]
+    out = []
+    for k in range(config.MODEL.NUM_KEYPOINTS):
+        rows = line[po[k]:po[k + 1]]
+        arr = np.zeros((len(rows), 4))
+        arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3] = rows["x"], rows["y"], rows["score"], rows["id"]
+        out.append(arr)
+    return out
