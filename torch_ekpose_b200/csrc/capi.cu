@@ -19,6 +19,7 @@ namespace ekp {
 size_t dense_frontend_smem_bytes(int tile_wl);
 int dense_frontend_tile_wl(int w);
 cudaError_t configure_dense_frontend();
+cudaError_t set_interior_taps(const float* taps64);
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream);
 cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream);
 cudaError_t launch_upsample_nearest(const float* lo, int layout, int n, int h, int w, int C, float* out, cudaStream_t stream);
@@ -221,6 +222,11 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
     e = cudaMemcpy(c->cubic, cubic, sizeof(cubic), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = configure_dense_frontend();
+    if (e == cudaSuccess) {  // taps of interior rows/columns depend only on the phase (D & 7): constant memory
+        std::vector<float> t8;
+        build_dense_taps(8, t8);
+        e = set_interior_taps(t8.data() + 16 * 8);
+    }
     if (e == cudaSuccess) e = configure_peaks_sort(max_peaks);
     if (e == cudaSuccess) e = configure_assemble(max_humans);
     if (e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "context setup: %s", cudaGetErrorString(e)); }
@@ -238,6 +244,13 @@ static int ensure_tables(ekp_ctx* c, int h, int w, cudaStream_t stream) {
     if (c->tab_h == h && c->tab_w == w) return EKP_OK;
     std::vector<float> tx, ty;
     if (build_dense_taps(w, tx) || build_dense_taps(h, ty)) return fail(EKP_ERR_ARG, "dense front-end needs h, w >= 5 (got %dx%d)", h, w);
+    {   // the kernel reads interior row blocks (2 <= m <= h-3) from the phase table in constant memory
+        std::vector<float> t8;
+        build_dense_taps(8, t8);
+        for (int Y = 16; Y < 8 * (h - 2); Y++)
+            if (memcmp(&ty[(size_t) Y * 8], &t8[(size_t) (16 + (Y & 7)) * 8], 8 * sizeof(float)) != 0)
+                return fail(EKP_ERR_STATE, "internal: interior taps are not periodic at row %d", Y);
+    }
     CU(cudaStreamSynchronize(stream));  // nothing in flight may still read the old tables
     if (c->ax) { cudaFree(c->ax); c->ax = nullptr; }
     if (c->ay) { cudaFree(c->ay); c->ay = nullptr; }
