@@ -89,7 +89,13 @@ static int build_dense_taps(int n, std::vector<float>& taps) {
         if (base > n - 5) base = n - 5;
         for (int i = 0; i < n; i++)
             if (row[i] != 0.0 && (i < base || i >= base + 5)) return -2;  // support must fit the window
-        for (int k = 0; k < 5; k++) taps[(size_t) D * 8 + k] = (float) row[base + k];
+        double tsum = 0.0;
+        for (int k = 0; k < 5; k++) {
+            taps[(size_t) D * 8 + k] = (float) row[base + k];
+            if (row[base + k] < 0.0) return -3;
+            tsum += (double) taps[(size_t) D * 8 + k];
+        }
+        if (tsum > 1.0 + 1e-6) return -3;  // the kernel's early-out relies on convex weights
     }
     return 0;
 }

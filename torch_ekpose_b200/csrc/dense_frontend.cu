@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
             materialise_tile<EKP_HEAT_CH>(sHeat, hr0, hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0, tb, i0, twl);
     }
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler too
     const int TW = 8 * twl, X0 = 8 * i0;
     const int nstrips = (TW + 29) / 30;
     const unsigned m_strips = magic_of(nstrips);
@@ -234,6 +235,23 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
         const float4 axv = __ldg(reinterpret_cast<const float4*>(p.ax + (size_t) Xc * 8));
         const float ax4 = __ldg(p.ax + (size_t) Xc * 8 + 4);
         const float* colp = sHeat + (bx - hc0) * EKP_HEAT_CH + c - hr0 * rstride;
+
+        if (!kDebug && p.thr > 0.f) {
+            // Exact early-out.  All taps are >= 0 and sum to 1 (checked on the host), so every smoothed
+            // value this warp can produce is a convex combination of the staged stride-8 samples in
+            // columns [bx(first lane), bx(last lane) + 4]: if their maximum is below the threshold
+            // (by more than the rounding slack of ten float operations) no pixel here can pass
+            // `S > thr`, hence no peak, and the smoothing + NMS of this strip is skipped.
+            const int c_lo = __shfl_sync(0xffffffffu, bx, 0), c_hi = __shfl_sync(0xffffffffu, bx, 31) + 4;
+            const int ncol = c_hi - c_lo + 1, nrow = hr1 - hr0 + 1;
+            float mx = 0.f;
+            for (int idx = lane; idx < ncol * nrow; idx += 32) {
+                const int r = idx / ncol, i = idx - r * ncol;
+                mx = fmaxf(mx, sHeat[(r * hcols + (c_lo - hc0 + i)) * EKP_HEAT_CH + c]);
+            }
+            const int mxi = __reduce_max_sync(0xffffffffu, __float_as_int(mx));  // mx >= 0: integer order == float order
+            if (__int_as_float(mxi) <= p.thr * 0.99999f) continue;
+        }
 
         auto trow = [&](int j) -> float {  // horizontal 5-tap pass on stride-8 row j
             const float* s = colp + j * rstride;
