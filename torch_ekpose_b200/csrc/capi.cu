@@ -30,9 +30,9 @@ cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_
                               int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
 cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int max_peaks, const PafSource& paf, int h1, int n,
                                Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream);
-cudaError_t configure_assemble(int max_humans);
-cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const Conn* conns, const int* n_conns, int max_humans, int n,
-                            float* subset_out, int* num_humans, ekp_peak* hparts, float* hscore, unsigned* overflow,
+cudaError_t configure_assemble(int max_humans, int max_peaks);
+cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,
+                            int max_humans, int n, const unsigned* overflow, unsigned char* records, const ResultLayout& lay,
                             cudaStream_t stream);
 }  // namespace ekp
 
@@ -126,10 +126,8 @@ struct ekp_ctx {
     int* n_peaks = nullptr;         // [max_batch]
     Conn* conns = nullptr;          // [max_batch][19][EKP_MAX_PART]
     int* n_conns = nullptr;         // [max_batch][19]
-    float* subset = nullptr;        // [max_batch][max_humans][20]
-    int* num_humans = nullptr;      // [max_batch]
-    ekp_peak* hparts = nullptr;     // [max_batch][max_humans][18]
-    float* hscore = nullptr;        // [max_batch][max_humans]
+    unsigned char* records = nullptr;  // [max_batch] packed result records (ResultLayout)
+    ResultLayout lay = {};
     float* in_heat = nullptr;       // staging for the host-buffer entry points
     float* in_paf = nullptr;
     float* mat_heat = nullptr;      // context-owned operator-surface tensors (host entry, lazily)
@@ -140,12 +138,7 @@ struct ekp_ctx {
     int tab_h = 0, tab_w = 0;
     float* cubic = nullptr;         // [8][4]
     // pinned host mirrors of the results
-    int* h_num_humans = nullptr;
-    int* h_n_peaks = nullptr;
-    unsigned* h_overflow = nullptr;
-    float* h_subset = nullptr;
-    ekp_peak* h_hparts = nullptr;
-    float* h_hscore = nullptr;
+    unsigned char* h_records = nullptr;
     ekp_peak* h_line = nullptr;
     cudaEvent_t done = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -166,10 +159,10 @@ static inline void mark(ekp_ctx* c, int k, cudaStream_t st) {
 static int ctx_free(ekp_ctx* c) {
     if (!c) return EKP_OK;
     cudaSetDevice(c->device);
-    void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->subset, c->num_humans,
-                   c->hparts, c->hscore, c->in_heat, c->in_paf, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic};
+    void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->records,
+                   c->in_heat, c->in_paf, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic};
     for (void* p : dev) if (p) cudaFree(p);
-    void* host[] = {c->h_num_humans, c->h_n_peaks, c->h_overflow, c->h_subset, c->h_hparts, c->h_hscore, c->h_line};
+    void* host[] = {c->h_records, c->h_line};
     for (void* p : host) if (p) cudaFreeHost(p);
     if (c->done) cudaEventDestroy(c->done);
     for (auto& row : c->tev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
@@ -180,8 +173,8 @@ static int ctx_free(ekp_ctx* c) {
 extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, int max_w, int max_peaks, int max_humans) {
     if (!out) return fail(EKP_ERR_ARG, "ekp_create: out is NULL");
     *out = nullptr;
-    if (max_batch < 1 || max_h < 5 || max_w < 5 || max_peaks < 1 || max_humans < 1 || max_peaks > 16384 || max_humans > 2048)
-        return fail(EKP_ERR_ARG, "ekp_create: bad capacity (batch %d, map %dx%d >= 5x5, peaks %d <= 16384, humans %d <= 2048)",
+    if (max_batch < 1 || max_h < 5 || max_w < 5 || max_peaks < 1 || max_humans < 1 || max_peaks > 16384 || max_humans > 1024)
+        return fail(EKP_ERR_ARG, "ekp_create: bad capacity (batch %d, map %dx%d >= 5x5, peaks %d <= 16384, humans %d <= 1024)",
                     max_batch, max_h, max_w, max_peaks, max_humans);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -211,17 +204,13 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
     DEV_ALLOC(c->n_peaks, sizeof(int) * B);
     DEV_ALLOC(c->conns, sizeof(Conn) * B * EKP_NUM_LIMB * EKP_MAX_PART);
     DEV_ALLOC(c->n_conns, sizeof(int) * B * EKP_NUM_LIMB);
-    DEV_ALLOC(c->subset, sizeof(float) * B * max_humans * 20);
-    DEV_ALLOC(c->num_humans, sizeof(int) * B);
-    DEV_ALLOC(c->hparts, sizeof(ekp_peak) * B * max_humans * EKP_NUM_PART);
-    DEV_ALLOC(c->hscore, sizeof(float) * B * max_humans);
+    c->lay.off_subset = 16;
+    c->lay.off_hparts = c->lay.off_subset + sizeof(float) * 20 * (size_t) max_humans;
+    c->lay.off_hscore = c->lay.off_hparts + sizeof(ekp_peak) * EKP_NUM_PART * (size_t) max_humans;
+    c->lay.stride = (c->lay.off_hscore + sizeof(float) * (size_t) max_humans + 15) & ~(size_t) 15;
+    DEV_ALLOC(c->records, c->lay.stride * B);
     DEV_ALLOC(c->cubic, sizeof(float) * 32);
-    HOST_ALLOC(c->h_num_humans, sizeof(int) * B);
-    HOST_ALLOC(c->h_n_peaks, sizeof(int) * B);
-    HOST_ALLOC(c->h_overflow, sizeof(unsigned) * B);
-    HOST_ALLOC(c->h_subset, sizeof(float) * B * max_humans * 20);
-    HOST_ALLOC(c->h_hparts, sizeof(ekp_peak) * B * max_humans * EKP_NUM_PART);
-    HOST_ALLOC(c->h_hscore, sizeof(float) * B * max_humans);
+    HOST_ALLOC(c->h_records, c->lay.stride * B);
     HOST_ALLOC(c->h_line, sizeof(ekp_peak) * B * max_peaks);
     float cubic[32];
     build_cubic_table(cubic);
@@ -234,7 +223,7 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
         e = set_interior_taps(t8.data() + 16 * 8);
     }
     if (e == cudaSuccess) e = configure_peaks_sort(max_peaks);
-    if (e == cudaSuccess) e = configure_assemble(max_humans);
+    if (e == cudaSuccess) e = configure_assemble(max_humans, max_peaks);
     if (e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "context setup: %s", cudaGetErrorString(e)); }
     *out = c;
     return EKP_OK;
@@ -286,17 +275,12 @@ static int run_back_half(ekp_ctx* c, int n, int id_from_key, const PafSource& pa
     mark(c, 2, st);
     CU(launch_paf_connect(c->line, c->part_off, c->max_peaks, paf, h1, n, c->conns, c->n_conns, c->overflow, st));
     mark(c, 3, st);
-    CU(launch_assemble(c->line, c->max_peaks, c->conns, c->n_conns, c->max_humans, n, c->subset, c->num_humans, c->hparts,
-                       c->hscore, c->overflow, st));
+    CU(launch_assemble(c->line, c->max_peaks, c->n_peaks, c->conns, c->n_conns, c->max_humans, n, c->overflow, c->records,
+                       c->lay, st));
     mark(c, 4, st);
     if (c->timing) c->timed_runs++;
     c->launches += 3;
-    CU(cudaMemcpyAsync(c->h_num_humans, c->num_humans, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_n_peaks, c->n_peaks, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_overflow, c->overflow, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_subset, c->subset, sizeof(float) * 20 * (size_t) n * c->max_humans, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_hparts, c->hparts, sizeof(ekp_peak) * EKP_NUM_PART * (size_t) n * c->max_humans, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_hscore, c->hscore, sizeof(float) * (size_t) n * c->max_humans, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_records, c->records, c->lay.stride * (size_t) n, cudaMemcpyDeviceToHost, st));  // one packed copy
     CU(cudaEventRecord(c->done, st));
     c->last_stream = st; c->last_n = n; c->has_run = true;
     return EKP_OK;
@@ -395,9 +379,12 @@ static int wait_results(ekp_ctx* c, const char* who) {
     CU(cudaEventSynchronize(c->done));
     return EKP_OK;
 }
+struct RecHead { int num_humans, n_peaks; unsigned overflow; int pad; };
+static const RecHead* rec_head(const ekp_ctx* c, int i) { return reinterpret_cast<const RecHead*>(c->h_records + c->lay.stride * (size_t) i); }
+
 static int overflow_status(const ekp_ctx* c) {
     unsigned any = 0;
-    for (int i = 0; i < c->last_n; i++) any |= c->h_overflow[i];
+    for (int i = 0; i < c->last_n; i++) any |= rec_head(c, i)->overflow;
     if (any & EKP_OVF_BADPEAK) return fail(EKP_ERR_ARG, "a peak has part id outside [0,18), coordinates outside the PAF map, or a NaN score");
     if (any) return fail(EKP_ERR_CAPACITY, "capacity overflow (bits 0x%x: 1 peaks>%d, 2 part>%d, 4 candidates>%d, 8 humans>%d)", any,
                          c->max_peaks, EKP_MAX_PART, EKP_MAX_CAND, c->max_humans);
@@ -408,10 +395,15 @@ extern "C" int ekp_results(ekp_ctx* c, int* num_humans, float* subset, int* n_pe
     int rc = wait_results(c, "ekp_results");
     if (rc) return rc;
     const int n = c->last_n;
-    if (num_humans) memcpy(num_humans, c->h_num_humans, sizeof(int) * n);
-    if (n_peaks) memcpy(n_peaks, c->h_n_peaks, sizeof(int) * n);
-    if (overflow) memcpy(overflow, c->h_overflow, sizeof(unsigned) * n);
-    if (subset) memcpy(subset, c->h_subset, sizeof(float) * 20 * (size_t) n * c->max_humans);
+    const size_t mh = (size_t) c->max_humans;
+    for (int i = 0; i < n; i++) {
+        const RecHead* hd = rec_head(c, i);
+        if (num_humans) num_humans[i] = hd->num_humans;
+        if (n_peaks) n_peaks[i] = hd->n_peaks;
+        if (overflow) overflow[i] = hd->overflow;
+        if (subset) memcpy(subset + (size_t) i * mh * 20, c->h_records + c->lay.stride * (size_t) i + c->lay.off_subset,
+                           sizeof(float) * 20 * (size_t) hd->num_humans);
+    }
     if (peaks_line) {  // the big table is only fetched on request
         CU(cudaMemcpyAsync(c->h_line, c->line, sizeof(ekp_peak) * (size_t) n * c->max_peaks, cudaMemcpyDeviceToHost, c->last_stream));
         CU(cudaStreamSynchronize(c->last_stream));
@@ -424,10 +416,15 @@ extern "C" int ekp_results_humans(ekp_ctx* c, int* num_humans, ekp_peak* parts, 
     int rc = wait_results(c, "ekp_results_humans");
     if (rc) return rc;
     const int n = c->last_n;
-    if (num_humans) memcpy(num_humans, c->h_num_humans, sizeof(int) * n);
-    if (overflow) memcpy(overflow, c->h_overflow, sizeof(unsigned) * n);
-    if (parts) memcpy(parts, c->h_hparts, sizeof(ekp_peak) * EKP_NUM_PART * (size_t) n * c->max_humans);
-    if (scores) memcpy(scores, c->h_hscore, sizeof(float) * (size_t) n * c->max_humans);
+    const size_t mh = (size_t) c->max_humans;
+    for (int i = 0; i < n; i++) {
+        const RecHead* hd = rec_head(c, i);
+        const unsigned char* rec = c->h_records + c->lay.stride * (size_t) i;
+        if (num_humans) num_humans[i] = hd->num_humans;
+        if (overflow) overflow[i] = hd->overflow;
+        if (parts) memcpy(parts + (size_t) i * mh * EKP_NUM_PART, rec + c->lay.off_hparts, sizeof(ekp_peak) * EKP_NUM_PART * (size_t) hd->num_humans);
+        if (scores) memcpy(scores + (size_t) i * mh, rec + c->lay.off_hscore, sizeof(float) * (size_t) hd->num_humans);
+    }
     return overflow_status(c);
 }
 
@@ -554,7 +551,8 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
         if (rc) return rc;
         g_num_humans = nh;
         g_subset.assign(subset.begin(), subset.begin() + (size_t) nh * 20);
-        g_hscore.assign(c->h_hscore, c->h_hscore + nh);
+        const float* hs = reinterpret_cast<const float*>(c->h_records + c->lay.off_hscore);
+        g_hscore.assign(hs, hs + nh);
         g_line.assign(line.begin(), line.begin() + np);
         return EKP_OK;  // the reference returns 0 (pafprocess.cpp:193)
     }

@@ -66,6 +66,15 @@ __device__ __forceinline__ float lo_at(const float* lo, int layout, int img, int
                                      : __ldg(lo + (((size_t) img * h + j) * w + i) * C + c);
 }
 
+// One packed result record per image, so a batch's results are a single device-to-host copy:
+//   [0]           int num_humans, int n_peaks, unsigned overflow, int pad
+//   [off_subset]  float  subset[max_humans][20]      rows as the reference keeps them
+//   [off_hparts]  ekp_peak parts[max_humans][18]     (x, y, score, cid or -1) per human and part
+//   [off_hscore]  float  score[max_humans]           subset[18] / subset[19]
+struct ResultLayout {
+    size_t stride, off_subset, off_hparts, off_hscore;
+};
+
 // launch parameter blocks --------------------------------------------------------------------
 struct DenseParams {
     const float* heat;

@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     __shared__ ekp_peak sA[EKP_MAX_PART], sB[EKP_MAX_PART];
     __shared__ float sScore[EKP_MAX_CAND];
     __shared__ unsigned sTag[EKP_MAX_CAND];
+    __shared__ float sScore2[EKP_MAX_CAND];
+    __shared__ unsigned sTag2[EKP_MAX_CAND];
+    __shared__ int sTies;
     __shared__ int sWarpCnt[kConnThreads / 32];
     const int limb = blockIdx.x, img = blockIdx.y;
     const int pa = kPairs[limb][0], pb = kPairs[limb][1];
@@ -257,26 +260,55 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
         __syncthreads();
     }
 
+    // ---- sort (pafprocess.cpp:97).  std::sort's result is only algorithm-dependent in how it
+    // permutes EQUAL scores, and for n <= 16 it is a plain (stable) insertion sort.  So: rank every
+    // candidate in parallel (stable order) and detect ties; only when n > 16 AND ties exist does
+    // one thread replay libstdc++'s introsort on the original sequence.
+    const int n = min(total, EKP_MAX_CAND);
     if (threadIdx.x == 0) {
-        if (total > EKP_MAX_CAND) { atomicOr(overflow + img, EKP_OVF_CANDIDATES); total = EKP_MAX_CAND; }
-        CandArray A;
-        A.s = sScore; A.t = sTag;
-        std_sort_desc(A, total);
+        sTies = 0;
+        if (total > EKP_MAX_CAND) atomicOr(overflow + img, EKP_OVF_CANDIDATES);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kConnThreads) {
+        const float s = sScore[i];
+        int rank = 0;
+        bool tie = false;
+        for (int j = 0; j < n; j++) {
+            const float sj = sScore[j];
+            rank += (sj > s) || (sj == s && j < i);
+            tie |= (sj == s) && (j != i);
+        }
+        sScore2[rank] = s;
+        sTag2[rank] = sTag[i];
+        if (tie) sTies = 1;
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        const float* srcS = sScore2;
+        const unsigned* srcT = sTag2;
+        if (n > 16 && sTies) {
+            CandArray A;
+            A.s = sScore; A.t = sTag;
+            std_sort_desc(A, n);
+            srcS = sScore; srcT = sTag;
+        }
         // greedy assignment, pafprocess.cpp:98-124 (a peak is used at most once per limb side)
         unsigned usedA[EKP_MAX_PART / 32], usedB[EKP_MAX_PART / 32];
 #pragma unroll
         for (int k = 0; k < EKP_MAX_PART / 32; k++) usedA[k] = usedB[k] = 0u;
         Conn* out = conns + ((size_t) img * EKP_NUM_LIMB + limb) * EKP_MAX_PART;
         int nc = 0;
-        for (int c = 0; c < total; c++) {
-            const unsigned tag = sTag[c];
+        for (int c = 0; c < n; c++) {
+            const unsigned tag = srcT[c];
             const int i1 = tag >> 16, i2 = tag & 0xffff;
             if ((usedA[i1 >> 5] >> (i1 & 31)) & 1u) continue;
             if ((usedB[i2 >> 5] >> (i2 & 31)) & 1u) continue;
             usedA[i1 >> 5] |= 1u << (i1 & 31);
             usedB[i2 >> 5] |= 1u << (i2 & 31);
             Conn cn;
-            cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = sScore[c]; cn.pad = 0;
+            cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c]; cn.pad = 0;
             out[nc++] = cn;
         }
         *out_n = nc;
