@@ -9,66 +9,129 @@
 // connection matching three or more rows is dropped, limb 18 never starts a person, and peak
 // scores are looked up by cid in the part-sorted table.
 //
-// The loop is latency bound, so everything it touches (the image's connections and peak scores)
-// is first staged in shared memory with coalesced loads; the serial part then only sees ~30-cycle
-// shared-memory latencies instead of dependent global loads.  Results go to one packed record per
-// image (ResultLayout) so the host needs a single device-to-host copy per batch.
+// A single warp running dependent code pays full latency on every instruction, so:
+//  * the image's connections and peak scores are staged in shared memory first (coalesced);
+//  * while the image has at most 32 candidate people, lane r keeps subset row r in REGISTERS
+//    (the 19-limb loop is unrolled so every column index is a compile-time constant); a
+//    connection then costs one broadcast load, two compares and a ballot.  A 33rd row restarts
+//    the image on the general shared-memory path below (same arithmetic, any row count);
+//  * results go to one packed record per image (ResultLayout): one device-to-host copy per batch.
 #include "common.cuh"
 
 namespace ekp {
 
-__global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict__ line, int max_peaks,
-                                                      const int* __restrict__ n_peaks, const Conn* __restrict__ conns,
-                                                      const int* __restrict__ n_conns, int max_humans, int conn_cap,
-                                                      int score_cap, const unsigned* __restrict__ overflow,
-                                                      unsigned char* __restrict__ records, ResultLayout lay) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* rows = reinterpret_cast<float*>(smem_raw);                        // [max_humans][20]
-    Conn* sConn = reinterpret_cast<Conn*>(rows + (size_t) max_humans * 20);   // [conn_cap]
-    float* sScore = reinterpret_cast<float*>(sConn + conn_cap);              // [score_cap]
-    __shared__ int sStart[EKP_NUM_LIMB + 1];
+// pafprocess.h:21-24 as compile-time constants for the unrolled fast path
+__host__ __device__ constexpr int limb_a(int l) {
+    constexpr int t[EKP_NUM_LIMB] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
+    return t[l];
+}
+__host__ __device__ constexpr int limb_b(int l) {
+    constexpr int t[EKP_NUM_LIMB] = {2, 5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 0, 14, 16, 15, 17, 16, 17};
+    return t[l];
+}
 
-    const int img = blockIdx.x, lane = threadIdx.x;
-    const ekp_peak* L = line + (size_t) img * max_peaks;
-    const int npk = n_peaks[img];
+struct AsmInput {
+    const Conn* sConn;    // staged connections (or nullptr -> read `conns`)
+    const int* sStart;    // [20] prefix of per-limb counts
+    const float* sScore;  // staged peak scores (or nullptr -> read `L`)
+    const Conn* conns;    // this image's [19][EKP_MAX_PART]
+    const ekp_peak* L;    // this image's part-sorted peak table
+    __device__ __forceinline__ Conn conn_at(int limb, int k) const {
+        return sConn ? sConn[sStart[limb] + k] : conns[(size_t) limb * EKP_MAX_PART + k];
+    }
+    __device__ __forceinline__ float score_of(int cid) const { return sScore ? sScore[cid] : L[cid].score; }
+};
 
-    // ---- stage connections and peak scores --------------------------------------------------
-    int cnt = 0;
-    if (lane < EKP_NUM_LIMB) cnt = min(n_conns[(size_t) img * EKP_NUM_LIMB + lane], EKP_MAX_PART);
-    int incl = cnt;  // inclusive prefix over the 19 limbs
+// ---- fast path: one subset row per lane, in registers ------------------------------------------
+// Returns false (rows/nrows undefined) when a 33rd row would be needed.
+__device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float* __restrict__ rows_out, int& nrows_out) {
+    const int lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    float r[20];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane < EKP_NUM_LIMB) sStart[lane] = incl - cnt;
-    if (lane == EKP_NUM_LIMB - 1) sStart[EKP_NUM_LIMB] = incl;
-    __syncwarp();
-    const int total_conns = sStart[EKP_NUM_LIMB];
-    const bool staged = total_conns <= conn_cap && npk <= score_cap;
-    if (staged) {
-        for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
-            const int s0 = sStart[limb], n = sStart[limb + 1] - s0;
-            const Conn* C = conns + ((size_t) img * EKP_NUM_LIMB + limb) * EKP_MAX_PART;
-            for (int k = lane; k < n; k += 32) sConn[s0 + k] = C[k];
-        }
-        for (int k = lane; k < npk; k += 32) sScore[k] = L[k].score;
-    }
-    __syncwarp();
-
-    auto conn_at = [&](int limb, int k) -> Conn {
-        return staged ? sConn[sStart[limb] + k] : conns[((size_t) img * EKP_NUM_LIMB + limb) * EKP_MAX_PART + k];
-    };
-    auto score_of = [&](int cid) -> float { return staged ? sScore[cid] : L[cid].score; };
-
-    // ---- sequential assembly ------------------------------------------------------------------
+    for (int q = 0; q < 20; q++) r[q] = -1.0f;
     int nrows = 0;
-    bool ovf = false;
+    const int cap = max_humans < 32 ? max_humans : 32;
+    bool fits = true;
+#pragma unroll
+    for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
+        const int p1 = limb_a(limb), p2 = limb_b(limb);
+        const int nc = in.sStart[limb + 1] - in.sStart[limb];
+        for (int k = 0; k < nc; k++) {
+            const Conn cn = in.conn_at(limb, k);
+            const float f1 = (float) cn.cid1, f2 = (float) cn.cid2;
+            const bool m = lane < nrows && (r[p1] == f1 || r[p2] == f2);
+            unsigned mask = __ballot_sync(FULL, m);
+            const int found = __popc(mask);
+            if (found == 1) {
+                if (m && r[p2] != f2) {
+                    r[p2] = f2;
+                    r[19] = __fadd_rn(r[19], 1.0f);
+                    r[18] = __fadd_rn(r[18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                }
+            } else if (found == 2) {
+                const int s1 = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int s2 = __ffs(mask) - 1;
+                bool both = false;
+                float o[20];
+#pragma unroll
+                for (int q = 0; q < 20; q++) o[q] = __shfl_sync(FULL, r[q], s2);
+#pragma unroll
+                for (int q = 0; q < 18; q++) both |= (r[q] > 0.f && o[q] > 0.f);
+                const bool membership = __shfl_sync(FULL, (int) both, s1) != 0;
+                if (!membership) {
+                    if (lane == s1) {
+#pragma unroll
+                        for (int q = 0; q < 18; q++) r[q] = __fadd_rn(r[q], __fadd_rn(o[q], 1.0f));
+                        r[19] = __fadd_rn(r[19], o[19]);
+                        r[18] = __fadd_rn(__fadd_rn(r[18], o[18]), cn.score);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 20; q++) {  // erase row s2: rows above it move down one lane
+                        const float nx = __shfl_down_sync(FULL, r[q], 1);
+                        if (lane >= s2) r[q] = nx;
+                    }
+                    nrows--;
+                } else if (lane == s1) {
+                    r[p2] = f2;
+                    r[19] = __fadd_rn(r[19], 1.0f);
+                    r[18] = __fadd_rn(r[18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                }
+            } else if (found == 0 && limb < 18) {
+                if (nrows >= cap) { fits = false; break; }
+                if (lane == nrows) {
+#pragma unroll
+                    for (int q = 0; q < 18; q++) r[q] = -1.0f;
+                    r[p1] = f1;
+                    r[p2] = f2;
+                    r[19] = 2.0f;
+                    r[18] = __fadd_rn(__fadd_rn(in.score_of(cn.cid1), in.score_of(cn.cid2)), cn.score);
+                }
+                nrows++;
+            }
+        }
+        if (!fits) break;
+    }
+    if (!fits) return false;
+    if (lane < nrows) {
+#pragma unroll
+        for (int q = 0; q < 20; q++) rows_out[lane * 20 + q] = r[q];
+    }
+    nrows_out = nrows;
+    __syncwarp();
+    return true;
+}
+
+// ---- general path: rows in shared memory, any count up to max_humans ---------------------------
+__device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __restrict__ rows, int& nrows_out, bool& ovf) {
+    const int lane = threadIdx.x;
+    int nrows = 0;
     for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
         const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
-        const int nc = sStart[limb + 1] - sStart[limb];
+        const int nc = in.sStart[limb + 1] - in.sStart[limb];
         for (int k = 0; k < nc; k++) {
-            const Conn cn = conn_at(limb, k);
+            const Conn cn = in.conn_at(limb, k);
             const float f1 = (float) cn.cid1, f2 = (float) cn.cid2;
             int found = 0, s1 = 0, s2 = 0;
             for (int base = 0; base < nrows; base += 32) {
@@ -91,7 +154,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
                 if (lane == 0 && rows[s1 * 20 + p2] != f2) {
                     rows[s1 * 20 + p2] = f2;
                     rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], __fadd_rn(score_of(cn.cid2), cn.score));
+                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], __fadd_rn(in.score_of(cn.cid2), cn.score));
                 }
             } else if (found == 2) {
                 const bool both = lane < 18 && rows[s1 * 20 + lane] > 0.f && rows[s2 * 20 + lane] > 0.f;
@@ -110,7 +173,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
                 } else if (lane == 0) {
                     rows[s1 * 20 + p2] = f2;
                     rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], __fadd_rn(score_of(cn.cid2), cn.score));
+                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], __fadd_rn(in.score_of(cn.cid2), cn.score));
                 }
             } else if (found == 0 && limb < 18) {
                 if (nrows < max_humans) {
@@ -119,7 +182,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
                         if (lane == p1) v = f1;
                         if (lane == p2) v = f2;
                         if (lane == 19) v = 2.0f;
-                        if (lane == 18) v = __fadd_rn(__fadd_rn(score_of(cn.cid1), score_of(cn.cid2)), cn.score);
+                        if (lane == 18) v = __fadd_rn(__fadd_rn(in.score_of(cn.cid1), in.score_of(cn.cid2)), cn.score);
                         rows[nrows * 20 + lane] = v;
                     }
                     nrows++;
@@ -130,27 +193,99 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
             __syncwarp();
         }
     }
+    nrows_out = nrows;
+}
+
+__global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict__ line, int max_peaks,
+                                                      const int* __restrict__ n_peaks, const Conn* __restrict__ conns,
+                                                      const int* __restrict__ n_conns, int max_humans, int conn_cap,
+                                                      int score_cap, const unsigned* __restrict__ overflow,
+                                                      unsigned char* __restrict__ records, ResultLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* rows = reinterpret_cast<float*>(smem_raw);                                        // [max(max_humans, 32)][20]
+    Conn* sConn = reinterpret_cast<Conn*>(rows + (size_t) (max_humans < 32 ? 32 : max_humans) * 20);  // [conn_cap]
+    float* sScore = reinterpret_cast<float*>(sConn + conn_cap);                              // [score_cap]
+    int* sKept = reinterpret_cast<int*>(sScore + score_cap);                                 // [max_humans]
+    __shared__ int sStart[EKP_NUM_LIMB + 1];
+
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const ekp_peak* L = line + (size_t) img * max_peaks;
+    const Conn* Cimg = conns + (size_t) img * EKP_NUM_LIMB * EKP_MAX_PART;
+    const int npk = n_peaks[img];
+
+    // ---- stage connections and peak scores --------------------------------------------------
+    int cnt = 0;
+    if (lane < EKP_NUM_LIMB) cnt = min(n_conns[(size_t) img * EKP_NUM_LIMB + lane], EKP_MAX_PART);
+    int incl = cnt;  // inclusive prefix over the 19 limbs
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane < EKP_NUM_LIMB) sStart[lane] = incl - cnt;
+    if (lane == EKP_NUM_LIMB - 1) sStart[EKP_NUM_LIMB] = incl;
+    __syncwarp();
+    const int total_conns = sStart[EKP_NUM_LIMB];
+    const bool staged = total_conns <= conn_cap && npk <= score_cap;
+    if (staged) {
+        // one flat pass so that all loads are in flight together (a per-limb loop would pay one
+        // global-memory round trip per limb)
+        for (int idx = lane; idx < total_conns; idx += 32) {
+            int limb = 0;
+#pragma unroll
+            for (int l = 1; l < EKP_NUM_LIMB; l++) limb += (idx >= sStart[l]);
+            sConn[idx] = Cimg[(size_t) limb * EKP_MAX_PART + (idx - sStart[limb])];
+        }
+        for (int k = lane; k < npk; k += 32) sScore[k] = L[k].score;
+    }
+    __syncwarp();
+    AsmInput in;
+    in.sConn = staged ? sConn : nullptr;
+    in.sStart = sStart;
+    in.sScore = staged ? sScore : nullptr;
+    in.conns = Cimg;
+    in.L = L;
+
+    // ---- sequential assembly ------------------------------------------------------------------
+    int nrows = 0;
+    bool ovf = false;
+    if (!assemble_in_registers(in, max_humans, rows, nrows)) assemble_in_smem(in, max_humans, rows, nrows, ovf);
+    __syncwarp();
 
     // ---- prune (pafprocess.cpp:187-191: a reverse erase loop == an order-preserving filter) and
-    //      write the image's result record ------------------------------------------------------
+    //      write the image's result record, all lanes busy --------------------------------------
     unsigned char* rec = records + (size_t) img * lay.stride;
     float* so = reinterpret_cast<float*>(rec + lay.off_subset);
     ekp_peak* hp = reinterpret_cast<ekp_peak*>(rec + lay.off_hparts);
     float* hs = reinterpret_cast<float*>(rec + lay.off_hscore);
     int kept = 0;
-    for (int r = 0; r < nrows; r++) {
-        const float c = rows[r * 20 + 19], sc = rows[r * 20 + 18];
-        if (c < 4.0f || __fdiv_rn(sc, c) < 0.3f) continue;
-        if (lane < 20) so[kept * 20 + lane] = rows[r * 20 + lane];
-        if (lane < EKP_NUM_PART) {
-            const int cid = (int) rows[r * 20 + lane];  // get_part_cid: float -> int
-            ekp_peak o;
-            if (cid >= 0) { const ekp_peak pk = L[cid]; o.x = pk.x; o.y = pk.y; o.score = pk.score; o.id = cid; }
-            else { o.x = 0; o.y = 0; o.score = 0.f; o.id = -1; }
-            hp[kept * EKP_NUM_PART + lane] = o;
+    for (int base = 0; base < nrows; base += 32) {
+        const int r = base + lane;
+        bool keep = false;
+        if (r < nrows) {
+            const float c = rows[r * 20 + 19], sc = rows[r * 20 + 18];
+            keep = !(c < 4.0f || __fdiv_rn(sc, c) < 0.3f);
         }
-        if (lane == 0) hs[kept] = __fdiv_rn(sc, c);  // get_score
-        kept++;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) sKept[kept + __popc(mask & ((1u << lane) - 1u))] = r;
+        kept += __popc(mask);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < kept * 20; idx += 32) {
+        const int k = idx / 20, q = idx - k * 20;
+        so[idx] = rows[sKept[k] * 20 + q];
+    }
+    for (int idx = lane; idx < kept * EKP_NUM_PART; idx += 32) {
+        const int k = idx / EKP_NUM_PART, q = idx - k * EKP_NUM_PART;
+        const int cid = (int) rows[sKept[k] * 20 + q];  // get_part_cid: float -> int
+        ekp_peak o;
+        if (cid >= 0) { const ekp_peak pk = L[cid]; o.x = pk.x; o.y = pk.y; o.score = pk.score; o.id = cid; }
+        else { o.x = 0; o.y = 0; o.score = 0.f; o.id = -1; }
+        hp[idx] = o;
+    }
+    for (int k = lane; k < kept; k += 32) {
+        const int r = sKept[k];
+        hs[k] = __fdiv_rn(rows[r * 20 + 18], rows[r * 20 + 19]);  // get_score
     }
     if (lane == 0) {
         int4 head;
@@ -163,7 +298,8 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
 }
 
 static size_t assemble_smem(int max_humans, int conn_cap, int score_cap) {
-    return sizeof(float) * 20 * (size_t) max_humans + sizeof(Conn) * (size_t) conn_cap + sizeof(float) * (size_t) score_cap;
+    const size_t nrow = (size_t) (max_humans < 32 ? 32 : max_humans);
+    return sizeof(float) * 20 * nrow + sizeof(Conn) * (size_t) conn_cap + sizeof(float) * (size_t) score_cap + sizeof(int) * nrow;
 }
 void assemble_caps(int max_peaks, int* conn_cap, int* score_cap) {
     *conn_cap = 2 * max_peaks < 2048 ? 2 * max_peaks : 2048;

@@ -308,6 +308,9 @@ extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, 
         p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.tile_wl = dense_frontend_tile_wl(w);
         CU(launch_dense_frontend(p, st));
         c->launches += 1;
+        // Stage 4 reads paf_mat exactly as the reference's process_paf does when it was materialised
+        // (2 loads per sample), else evaluates the same bilinear expression on the stride-8 PAF
+        // (8 loads per sample, bit-identical values: tests/test_gpu_parity.py).
         if (paf_mat) { src.ptr = paf_mat; src.mode = PAF_FULL_HWC; }
         else { src.ptr = paf; src.mode = PAF_LO_BILINEAR; }
     } else {
