@@ -236,7 +236,19 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout when the communicator is created; stdout must
+        # carry exactly one JSON line, so fd 1 points at stderr while the communicator comes up.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     # synthetic inputs: INPUT_SETS distinct batches per rank, resident in HBM and in pinned host memory
     sets_dev, sets_pin = [], []

@@ -30,7 +30,7 @@ constexpr int kThreads = 256;
 constexpr int kTH = 16;             // full-resolution rows per tile
 constexpr int kTB = kTH / 8;        // stride-8 row blocks per tile
 constexpr int kHeatRows = kTB + 6;  // stride-8 rows staged for the smoothing window
-constexpr int kPafRows = kTB + 2;   // rows staged for bilinear only
+constexpr int kPafRows = kTB + 1;   // rows staged for the tile's bilinear row pairs (m0-1 .. m0+tb-1)
 
 // Vertical taps of an interior row (no reflect / clamp influence) depend only on Y & 7.
 __constant__ float cTapsInterior[8][8];
@@ -119,22 +119,31 @@ __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, i
         };
 #pragma unroll
         for (int e = 0; e < 4; e++) bot[e] = 0.f;
+        // The tile materialises the rows of the stride-8 row PAIRS (m0-1, m0) .. (m0+tb-2, m0+tb-1),
+        // i.e. rows 8*m0-4 .. 8*(m0+tb)-5: each pair is complete (8 rows, one horizontal lerp per
+        // stride-8 row).  The clamped half pairs at the top and bottom of the image belong to the
+        // first and last tile.
         load_row(max(m0 - 1, 0));
-        float4* dst = reinterpret_cast<float4*>(out_img + ((size_t) (8 * m0) * W + X0) * C) + col;
-        // pair (m0-1, m0): its lower half (k = 4..7) are the tile's first four rows
+        const int Ystart = max(8 * m0 - 4, 0);
+        float4* dst = reinterpret_cast<float4*>(out_img + ((size_t) Ystart * W + X0) * C) + col;
         load_row(m0);
+        if (m0 == 0) {  // pair (-1, 0): only its lower half exists (rows 0..3)
 #pragma unroll
-        for (int k = 4; k < 8; k++) { store_row(dst, k); dst += stride4; }
-        // full pairs
+            for (int k = 4; k < 8; k++) { store_row(dst, k); dst += stride4; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { store_row(dst, k); dst += stride4; }
+        }
         for (int q = 1; q < tb; q++) {
             load_row(m0 + q);
 #pragma unroll
             for (int k = 0; k < 8; k++) { store_row(dst, k); dst += stride4; }
         }
-        // pair (m0+tb-1, m0+tb): its upper half (k = 0..3) are the tile's last four rows
-        load_row(min(m0 + tb, h - 1));
+        if (m0 + tb == h) {  // last tile: pair (h-1, h): only its upper half exists (rows 8h-4..8h-1)
+            load_row(h - 1);
 #pragma unroll
-        for (int k = 0; k < 4; k++) { store_row(dst, k); dst += stride4; }
+            for (int k = 0; k < 4; k++) { store_row(dst, k); dst += stride4; }
+        }
     }
 }
 
@@ -195,16 +204,26 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
 
     float* sHeat = smem;                                    // [kHeatRows][hcols][19]
     float* sPaf = sHeat + kHeatRows * hcols * EKP_HEAT_CH;  // [kPafRows][pcols][38]
+    float* sColMax = sPaf + kPafRows * pcols * EKP_PAF_CH;  // [hcols][19] max(0, column maximum over the staged rows)
 
     // the smoothing window of row block m is rows clamp(m-2, 0, h-5) .. +4 (same for columns)
     const int hr0 = max(min(m0 - 3, h - 5), 0), hr1 = min(max(m0 + tb + 2, 4), h - 1);
     const int hc0 = max(min(i0 - 3, w - 5), 0), hc1 = min(max(i0 + twl + 2, 4), w - 1);
-    const int pr0 = max(m0 - 1, 0), pr1 = min(m0 + tb, h - 1);
+    const int pr0 = max(m0 - 1, 0), pr1 = min(m0 + tb - 1, h - 1);
     const int pc0 = max(i0 - 1, 0), pc1 = min(i0 + twl, w - 1);
 
     stage_patch<EKP_HEAT_CH>(sHeat, p.heat, p.layout, img, h, w, hr0, hr1, hc0, hc1, hcols);
     if (kMat) stage_patch<EKP_PAF_CH>(sPaf, p.paf, p.layout, img, h, w, pr0, pr1, pc0, pc1, pcols);
     __syncthreads();
+    if (!kDebug) {  // per (column, channel) maximum of the staged heat samples, for the early-out below
+        const int ncolc = (hc1 - hc0 + 1) * EKP_HEAT_CH, nrow = hr1 - hr0 + 1;
+        for (int idx = threadIdx.x; idx < ncolc; idx += kThreads) {
+            float mx = 0.f;
+            for (int r = 0; r < nrow; r++) mx = fmaxf(mx, sHeat[r * hcols * EKP_HEAT_CH + idx]);
+            sColMax[idx] = mx;
+        }
+        __syncthreads();
+    }
 
     if (kMat) {
         materialise_tile<EKP_PAF_CH>(sPaf, pr0, pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0, twl);
@@ -239,16 +258,12 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
         if (!kDebug && p.thr > 0.f) {
             // Exact early-out.  All taps are >= 0 and sum to 1 (checked on the host), so every smoothed
             // value this warp can produce is a convex combination of the staged stride-8 samples in
-            // columns [bx(first lane), bx(last lane) + 4]: if their maximum is below the threshold
-            // (by more than the rounding slack of ten float operations) no pixel here can pass
-            // `S > thr`, hence no peak, and the smoothing + NMS of this strip is skipped.
+            // columns [bx(first lane), bx(last lane) + 4]: if their maximum (sColMax, over all staged
+            // rows) is below the threshold by more than the rounding slack of ten float operations,
+            // no pixel here can pass `S > thr`, hence no peak, and the strip is skipped.
             const int c_lo = __shfl_sync(0xffffffffu, bx, 0), c_hi = __shfl_sync(0xffffffffu, bx, 31) + 4;
-            const int ncol = c_hi - c_lo + 1, nrow = hr1 - hr0 + 1;
             float mx = 0.f;
-            for (int idx = lane; idx < ncol * nrow; idx += 32) {
-                const int r = idx / ncol, i = idx - r * ncol;
-                mx = fmaxf(mx, sHeat[(r * hcols + (c_lo - hc0 + i)) * EKP_HEAT_CH + c]);
-            }
+            if (c_lo + lane <= c_hi) mx = sColMax[(c_lo - hc0 + lane) * EKP_HEAT_CH + c];  // <= 13 columns
             const int mxi = __reduce_max_sync(0xffffffffu, __float_as_int(mx));  // mx >= 0: integer order == float order
             if (__int_as_float(mxi) <= p.thr * 0.99999f) continue;
         }
@@ -329,7 +344,8 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
 }
 
 size_t dense_frontend_smem_bytes(int tile_wl) {
-    return sizeof(float) * ((size_t) kHeatRows * (tile_wl + 6) * EKP_HEAT_CH + (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH);
+    return sizeof(float) * ((size_t) kHeatRows * (tile_wl + 6) * EKP_HEAT_CH + (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH +
+                            (size_t) (tile_wl + 6) * EKP_HEAT_CH);
 }
 
 // choose the stride-8 tile width: <= 32 columns, tiles of (nearly) equal width
