@@ -22,10 +22,19 @@
 // written for instruction count: interior row blocks take their vertical taps from constant
 // memory as immediate operands, eight rows are unrolled so the rolling NMS state is renamed
 // instead of moved, and index decoding in the staging loops uses multiply-high division.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ekp {
 
+#ifndef EKP_ROW_BATCH
+#define EKP_ROW_BATCH 4
+#endif
+#ifndef EKP_MIN_BLOCKS
+#define EKP_MIN_BLOCKS 3
+#endif
+constexpr int kRowBatch = EKP_ROW_BATCH;  // output rows whose stores are kept in flight together
 constexpr int kThreads = 256;
 constexpr int kTH = 16;             // full-resolution rows per tile
 constexpr int kTB = kTH / 8;        // stride-8 row blocks per tile
@@ -41,6 +50,17 @@ __host__ __device__ __forceinline__ unsigned magic_of(unsigned d) { return (unsi
 __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned magic) { return __umulhi(n, magic); }  // n, d < 2^16
 
 // ---- (1) stage a stride-8 patch in shared memory as [row][col][C] ----------------------------
+// Asynchronous 4-byte copies (cp.async / LDGSTS): a thread issues ALL of its ~37 element copies
+// back to back without holding registers, so the whole patch costs one global-memory round trip
+// instead of one per unrolled batch of loads.  The caller waits with stage_wait().
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
 template <int C>
 __device__ __forceinline__ void stage_patch(float* __restrict__ sP, const float* __restrict__ src, int layout,
                                             int img, int h, int w, int r0, int r1, int c0, int c1, int pcols) {
@@ -50,23 +70,21 @@ __device__ __forceinline__ void stage_patch(float* __restrict__ sP, const float*
         const unsigned m_plane = magic_of(plane), m_nc = magic_of(nc);  // uniform, a handful of instructions
         const float* g0 = src + ((size_t) img * C * h + r0) * w + c0;
         const int hw = h * w;
-#pragma unroll 4
         for (unsigned idx = threadIdx.x; idx < total; idx += kThreads) {
             const unsigned c = fastdiv(idx, m_plane);
             const unsigned rem = idx - c * plane;
             const unsigned r = fastdiv(rem, m_nc);
             const unsigned i = rem - r * nc;
-            sP[(r * pcols + i) * C + c] = __ldg(g0 + c * hw + r * w + i);
+            cp_async_f32(sP + (r * pcols + i) * C + c, g0 + c * hw + r * w + i);
         }
     } else {
         const unsigned per_r = nc * C, total = nr * per_r;
         const unsigned m_row = magic_of(per_r);
         const float* g0 = src + (((size_t) img * h + r0) * w + c0) * C;
-#pragma unroll 4
         for (unsigned idx = threadIdx.x; idx < total; idx += kThreads) {
             const unsigned r = fastdiv(idx, m_row);
             const unsigned rem = idx - r * per_r;
-            sP[r * pcols * C + rem] = __ldg(g0 + (size_t) r * w * C + rem);
+            cp_async_f32(sP + r * pcols * C + rem, g0 + (size_t) r * w * C + rem);
         }
     }
 }
@@ -108,14 +126,31 @@ __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, i
                 d[e] = __fsub_rn(bot[e], top[e]);
             }
         };
-        auto store_row = [&](float4* dst, int k) {  // output row with ty = (2k+1)/16
-            const float ty = (float) (2 * k + 1) * 0.0625f;
-            float4 v;
-            v.x = fmaf(ty, d[0], top[0]);
-            v.y = fmaf(ty, d[1], top[1]);
-            v.z = fmaf(ty, d[2], top[2]);
-            v.w = fmaf(ty, d[3], top[3]);
-            __stcs(dst, v);
+        // Rows k0 .. k0+NR-1 of the current pair (ty = (2k+1)/16).  All NR values are computed into
+        // distinct registers before the stores are issued: a store keeps its source registers busy
+        // until the LSU has accepted it, so reusing one float4 per row would allow only one store in
+        // flight per warp and starve the memory pipe (ncu: long-scoreboard stalls on the next FFMA).
+        auto store_rows = [&](float4*& dst, int k0, auto nr_tag) {
+            constexpr int NR = decltype(nr_tag)::value;
+            float4 v[NR];
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                const float ty = (float) (2 * (k0 + k) + 1) * 0.0625f;
+                v[k].x = fmaf(ty, d[0], top[0]);
+                v[k].y = fmaf(ty, d[1], top[1]);
+                v[k].z = fmaf(ty, d[2], top[2]);
+                v[k].w = fmaf(ty, d[3], top[3]);
+            }
+#pragma unroll
+            for (int k = 0; k < NR; k++) __stcs(dst + (size_t) k * stride4, v[k]);
+            dst += (size_t) NR * stride4;
+        };
+        auto store_range = [&](float4*& dst, auto k0_tag, auto n_tag) {  // n rows from k0, in batches of kRowBatch
+            constexpr int K0 = decltype(k0_tag)::value, NN = decltype(n_tag)::value;
+            constexpr int RB = kRowBatch < NN ? kRowBatch : NN;
+            static_assert(NN % RB == 0, "row batch must divide 4");
+#pragma unroll
+            for (int b = 0; b < NN / RB; b++) store_rows(dst, K0 + b * RB, std::integral_constant<int, RB>{});
         };
 #pragma unroll
         for (int e = 0; e < 4; e++) bot[e] = 0.f;
@@ -127,22 +162,18 @@ __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, i
         const int Ystart = max(8 * m0 - 4, 0);
         float4* dst = reinterpret_cast<float4*>(out_img + ((size_t) Ystart * W + X0) * C) + col;
         load_row(m0);
-        if (m0 == 0) {  // pair (-1, 0): only its lower half exists (rows 0..3)
-#pragma unroll
-            for (int k = 4; k < 8; k++) { store_row(dst, k); dst += stride4; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) { store_row(dst, k); dst += stride4; }
-        }
+        using I0 = std::integral_constant<int, 0>;
+        using I4 = std::integral_constant<int, 4>;
+        using I8 = std::integral_constant<int, 8>;
+        if (m0 == 0) store_range(dst, I4{}, I4{});  // pair (-1, 0): only its lower half exists (rows 0..3)
+        else store_range(dst, I0{}, I8{});
         for (int q = 1; q < tb; q++) {
             load_row(m0 + q);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { store_row(dst, k); dst += stride4; }
+            store_range(dst, I0{}, I8{});
         }
         if (m0 + tb == h) {  // last tile: pair (h-1, h): only its upper half exists (rows 8h-4..8h-1)
             load_row(h - 1);
-#pragma unroll
-            for (int k = 0; k < 4; k++) { store_row(dst, k); dst += stride4; }
+            store_range(dst, I0{}, I4{});
         }
     }
 }
@@ -192,8 +223,13 @@ __device__ __forceinline__ void nms_row(NmsState& st, float S, int X, int Y, boo
 }
 
 template <bool kMat, bool kDebug>
-__global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DenseParams p) {
+__global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kernel(const DenseParams p) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) float sTaps[64];  // interior taps by phase (copy of cTapsInterior for per-lane indexing)
+    __shared__ unsigned short sList[EKP_NUM_PART * 12];  // (part, strip) tasks that survive the early-out
+    __shared__ int sNumActive;
+    if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
+    if (threadIdx.x == 0) sNumActive = 0;
     const int img = blockIdx.z;
     const int m0 = blockIdx.y * kTB;
     const int i0 = blockIdx.x * p.tile_wl;
@@ -212,8 +248,20 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
     const int pr0 = max(m0 - 1, 0), pr1 = min(m0 + tb - 1, h - 1);
     const int pc0 = max(i0 - 1, 0), pc1 = min(i0 + twl, w - 1);
 
+    // The PAF patch (2/3 of the stores depend on it) is requested first and the heat patch second,
+    // as two cp.async groups: paf_mat is streamed out while the heat patch is still in flight.
+    if (kMat) {
+        stage_patch<EKP_PAF_CH>(sPaf, p.paf, p.layout, img, h, w, pr0, pr1, pc0, pc1, pcols);
+        stage_commit();
+    }
     stage_patch<EKP_HEAT_CH>(sHeat, p.heat, p.layout, img, h, w, hr0, hr1, hc0, hc1, hcols);
-    if (kMat) stage_patch<EKP_PAF_CH>(sPaf, p.paf, p.layout, img, h, w, pr0, pr1, pc0, pc1, pcols);
+    stage_commit();
+    if (kMat) {
+        stage_wait<1>();
+        __syncthreads();
+        materialise_tile<EKP_PAF_CH>(sPaf, pr0, pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0, twl);
+    }
+    stage_wait<0>();
     __syncthreads();
     if (!kDebug) {  // per (column, channel) maximum of the staged heat samples, for the early-out below
         const int ncolc = (hc1 - hc0 + 1) * EKP_HEAT_CH, nrow = hr1 - hr0 + 1;
@@ -222,14 +270,10 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
             for (int r = 0; r < nrow; r++) mx = fmaxf(mx, sHeat[r * hcols * EKP_HEAT_CH + idx]);
             sColMax[idx] = mx;
         }
-        __syncthreads();
     }
-
-    if (kMat) {
-        materialise_tile<EKP_PAF_CH>(sPaf, pr0, pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0, twl);
-        if (p.heat_mat)
-            materialise_tile<EKP_HEAT_CH>(sHeat, hr0, hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0, tb, i0, twl);
-    }
+    if (kMat && p.heat_mat)
+        materialise_tile<EKP_HEAT_CH>(sHeat, hr0, hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0, tb, i0, twl);
+    if (!kDebug) __syncthreads();  // sColMax complete
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler too
@@ -243,7 +287,33 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
     sink.count = p.raw_count + img;
     sink.cap = p.raw_cap;
 
-    for (int task = warp; task < EKP_NUM_PART * nstrips; task += kThreads / 32) {
+    // ---- exact early-out, decided once per (part, strip) by one thread each -------------------
+    // All taps are >= 0 and sum to 1 (checked on the host), so every smoothed value a strip can
+    // produce is a convex combination of the staged stride-8 samples in columns
+    // [bx(first lane), bx(last lane) + 4]: if their maximum (sColMax, over all staged rows) is below
+    // the threshold by more than the rounding slack of ten float operations, no pixel there can
+    // pass `S > thr`, hence no peak, and the strip is never visited.  Survivors go to a compact
+    // list that the warps then share evenly.
+    const int ntask = EKP_NUM_PART * nstrips;
+    for (int t = threadIdx.x; t < ntask; t += kThreads) {
+        const int c = (int) fastdiv(t, m_strips);
+        const int strip = t - c * nstrips;
+        bool active = kDebug || !(p.thr > 0.f);
+        if (!active) {
+            const int Xa = X0 - 1 + 30 * strip;
+            const int xlo = min(max(Xa, 0), min(W - 1, X0 + TW)), xhi = min(max(Xa + 31, 0), min(W - 1, X0 + TW));
+            const int c_lo = min(max((xlo >> 3) - 2, 0), w - 5), c_hi = min(max((xhi >> 3) - 2, 0), w - 5) + 4;
+            float mx = 0.f;
+            for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, sColMax[(i - hc0) * EKP_HEAT_CH + c]);
+            active = mx > p.thr * 0.99999f;
+        }
+        if (active) sList[atomicAdd(&sNumActive, 1)] = (unsigned short) t;
+    }
+    __syncthreads();
+    const int nactive = sNumActive;
+
+    for (int li = warp; li < nactive; li += kThreads / 32) {
+        const int task = sList[li];
         const int c = (int) fastdiv(task, m_strips);
         const int strip = task - c * nstrips;
         const int X = X0 - 1 + 30 * strip + lane;
@@ -251,23 +321,19 @@ __global__ void __launch_bounds__(kThreads) dense_frontend_kernel(const DensePar
         const bool out_lane = lane >= 1 && lane <= 30 && X < X0 + TW && X < W;
         const int Xc = min(max(X, 0), min(W - 1, X0 + TW));  // lanes past the halo are never outputs
         const int bx = min(max((Xc >> 3) - 2, 0), w - 5);
-        const float4 axv = __ldg(reinterpret_cast<const float4*>(p.ax + (size_t) Xc * 8));
-        const float ax4 = __ldg(p.ax + (size_t) Xc * 8 + 4);
         const float* colp = sHeat + (bx - hc0) * EKP_HEAT_CH + c - hr0 * rstride;
 
-        if (!kDebug && p.thr > 0.f) {
-            // Exact early-out.  All taps are >= 0 and sum to 1 (checked on the host), so every smoothed
-            // value this warp can produce is a convex combination of the staged stride-8 samples in
-            // columns [bx(first lane), bx(last lane) + 4]: if their maximum (sColMax, over all staged
-            // rows) is below the threshold by more than the rounding slack of ten float operations,
-            // no pixel here can pass `S > thr`, hence no peak, and the strip is skipped.
-            const int c_lo = __shfl_sync(0xffffffffu, bx, 0), c_hi = __shfl_sync(0xffffffffu, bx, 31) + 4;
-            float mx = 0.f;
-            if (c_lo + lane <= c_hi) mx = sColMax[(c_lo - hc0 + lane) * EKP_HEAT_CH + c];  // <= 13 columns
-            const int mxi = __reduce_max_sync(0xffffffffu, __float_as_int(mx));  // mx >= 0: integer order == float order
-            if (__int_as_float(mxi) <= p.thr * 0.99999f) continue;
+        // horizontal taps of this lane's column (only now: a skipped strip must not pay for the loads);
+        // interior columns take them from the phase table in shared memory, border columns from global
+        float4 axv;
+        float ax4;
+        if ((Xc >> 3) >= 2 && (Xc >> 3) <= w - 3) {
+            axv = *reinterpret_cast<const float4*>(sTaps + (Xc & 7) * 8);
+            ax4 = sTaps[(Xc & 7) * 8 + 4];
+        } else {
+            axv = __ldg(reinterpret_cast<const float4*>(p.ax + (size_t) Xc * 8));
+            ax4 = __ldg(p.ax + (size_t) Xc * 8 + 4);
         }
-
         auto trow = [&](int j) -> float {  // horizontal 5-tap pass on stride-8 row j
             const float* s = colp + j * rstride;
             float acc = __fmul_rn(axv.x, s[0]);
