@@ -59,3 +59,34 @@ def test_dims_validation_without_gpu():
             pp._dims(bad[0], bad[1], "nchw")
     with pytest.raises(ValueError):
         pp._dims((2, 19, 46, 54), (2, 38, 46, 54), "chwn")
+
+
+def test_coco_conversion_vectorised_equals_object_path():
+    """eval.py:93-125: the vectorised table path must equal the per-Human path bit for bit."""
+    from torch_ekpose_b200 import coco
+    rng = np.random.default_rng(0)
+    dt = np.dtype([("x", np.int32), ("y", np.int32), ("score", np.float32), ("id", np.int32)])
+    n, mh, H, W = 3, 5, 368, 432
+    num = np.array([2, 0, 5], np.int32)
+    parts = np.zeros((n, mh, 18), dt)
+    parts["x"], parts["y"] = rng.integers(0, W, (n, mh, 18)), rng.integers(0, H, (n, mh, 18))
+    parts["score"] = rng.random((n, mh, 18))
+    parts["id"] = np.where(rng.random((n, mh, 18)) < 0.7, rng.integers(0, 90, (n, mh, 18)), -1)
+    ups = [(368 / 0.77, 432 / 0.77), (368.0, 432.0), (368 / 1.3, 432 / 1.3)]
+    got = coco.coco_results([11, 12, 13], num, parts, (H, W), ups)
+    want = []
+    for i in range(n):
+        humans = []
+        for k in range(num[i]):
+            hm = Human([])
+            for p in range(18):
+                if parts[i, k, p]["id"] >= 0:
+                    hm.body_parts[p] = BodyPart("%d-%d" % (k, p), p, float(parts[i, k, p]["x"]) / W,
+                                                float(parts[i, k, p]["y"]) / H, float(parts[i, k, p]["score"]))
+            humans.append(hm)
+        coco.append_result(11 + i, humans, ups[i], want)
+    assert len(got) == len(want) == 7
+    for a, b in zip(got, want):
+        assert a["image_id"] == b["image_id"] and a["category_id"] == 1 and a["score"] == 1.0
+        assert len(a["keypoints"]) == 51 and a["keypoints"] == b["keypoints"]
+    assert coco.ORDER_COCO == [0, 15, 14, 17, 16, 5, 2, 6, 3, 7, 4, 11, 8, 12, 9, 13, 10]

@@ -34,8 +34,15 @@ namespace ekp {
 #ifndef EKP_MIN_BLOCKS
 #define EKP_MIN_BLOCKS 3
 #endif
+#ifndef EKP_THREADS
+#define EKP_THREADS 256
+#endif
+#ifndef EKP_MAX_TWL
+#define EKP_MAX_TWL 32
+#endif
 constexpr int kRowBatch = EKP_ROW_BATCH;  // output rows whose stores are kept in flight together
-constexpr int kThreads = 256;
+constexpr int kThreads = EKP_THREADS;
+constexpr int kMaxTwl = EKP_MAX_TWL;      // widest tile in stride-8 columns
 constexpr int kTH = 16;             // full-resolution rows per tile
 constexpr int kTB = kTH / 8;        // stride-8 row blocks per tile
 constexpr int kHeatRows = kTB + 6;  // stride-8 rows staged for the smoothing window
@@ -46,7 +53,8 @@ __constant__ float cTapsInterior[8][8];
 
 cudaError_t set_interior_taps(const float* taps64) { return cudaMemcpyToSymbol(cTapsInterior, taps64, sizeof(float) * 64); }
 
-__host__ __device__ __forceinline__ unsigned magic_of(unsigned d) { return (unsigned) ((0x100000000ull / d) + 1ull); }
+// floor(n / d) == __umulhi(n, magic_of(d)) for n * d < 2^32 (32-bit divide only: no 64-bit division subroutine)
+__host__ __device__ __forceinline__ unsigned magic_of(unsigned d) { return 0xFFFFFFFFu / d + 1u; }
 __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned magic) { return __umulhi(n, magic); }  // n, d < 2^16
 
 // ---- (1) stage a stride-8 patch in shared memory as [row][col][C] ----------------------------
@@ -226,7 +234,7 @@ template <bool kMat, bool kDebug>
 __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kernel(const DenseParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) float sTaps[64];  // interior taps by phase (copy of cTapsInterior for per-lane indexing)
-    __shared__ unsigned short sList[EKP_NUM_PART * 12];  // (part, strip) tasks that survive the early-out
+    __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];  // (part, strip) tasks that survive the early-out
     __shared__ int sNumActive;
     if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
     if (threadIdx.x == 0) sNumActive = 0;
@@ -414,15 +422,15 @@ size_t dense_frontend_smem_bytes(int tile_wl) {
                             (size_t) (tile_wl + 6) * EKP_HEAT_CH);
 }
 
-// choose the stride-8 tile width: <= 32 columns, tiles of (nearly) equal width
+// choose the stride-8 tile width: <= kMaxTwl columns, tiles of (nearly) equal width
 int dense_frontend_tile_wl(int w) {
-    const int nt = (w + 31) / 32;
+    const int nt = (w + kMaxTwl - 1) / kMaxTwl;
     return (w + nt - 1) / nt;
 }
 
 // per device, once (ekp_create): allow the largest tile's dynamic shared memory
 cudaError_t configure_dense_frontend() {
-    const int smem = (int) dense_frontend_smem_bytes(32);
+    const int smem = (int) dense_frontend_smem_bytes(kMaxTwl);
     cudaError_t e = cudaFuncSetAttribute(dense_frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_frontend_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_frontend_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
