@@ -339,3 +339,29 @@ def test_argument_errors(ek, pp):
     big = _dev(np.zeros((65, 19, 5, 5), np.float32)), _dev(np.zeros((65, 38, 5, 5), np.float32))
     with pytest.raises(ek._lib.EkpError):
         pp.run(*big, frontend="dense")
+
+
+@pytest.mark.parametrize("people", [20, 50, 100, 150])
+def test_assembly_paths_by_people_count(ek, people):
+    """20 / 50 / 100 / 150 four-part people in one image drive the assembly through its 32-, 64- and
+    128-row register paths and the shared-memory path; all must equal the oracle bit for bit."""
+    H, W = 32, 40 * people + 24
+    paf = np.zeros((1, H, W, 38), np.float32)
+    rows = []
+    rng = np.random.default_rng(people)
+    for i in range(people):
+        y, x0 = 8 + (i % 3) * 6, 8 + 40 * i
+        for k, part in enumerate((1, 2, 3, 4)):      # neck -> RShoulder -> RElbow -> RWrist, 8 px apart
+            rows.append((x0 + 8 * k, y, 0.5 + 0.4 * rng.random(), 0, part))
+        paf[0, y - 1:y + 2, x0 - 1:x0 + 26, 12] = 1     # limb 0 (1->2), 2 (2->3), 3 (3->4): x channels 12, 14, 16
+        paf[0, y - 1:y + 2, x0 - 1:x0 + 26, 14] = 1
+        paf[0, y - 1:y + 2, x0 - 1:x0 + 26, 16] = 1
+    peaks = np.array(rows, np.float32)
+    peaks = peaks[rng.permutation(len(peaks))][None]            # unsorted input on purpose
+    big = ek.PostProcessor(device=0, max_batch=1, max_h=8, max_w=8, max_peaks=1024, max_humans=256)
+    big.run_peaks(_dev(peaks), _dev(np.array([peaks.shape[1]], np.int32)), _dev(paf), h1=H)
+    res = big.results()
+    sub, _ = util.oracle_people(peaks[0], H, W, paf[0])
+    assert len(sub) == people == int(res["num_humans"][0])
+    assert_bits_equal(res["subset"][0, :people], sub, "subset")
+    big.close()

@@ -42,16 +42,20 @@ struct AsmInput {
     __device__ __forceinline__ float score_of(int cid) const { return sScore ? sScore[cid] : L[cid].score; }
 };
 
-// ---- fast path: one subset row per lane, in registers ------------------------------------------
-// Returns false (rows/nrows undefined) when a 33rd row would be needed.
+// ---- fast path: R subset rows per lane, in registers ------------------------------------------
+// Row index i lives in lane (i & 31), slot (i >> 5); capacity 32*R rows.  Returns false (outputs
+// undefined) when one more row would be needed; the caller then uses a larger R or the general path.
+template <int R>
 __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float* __restrict__ rows_out, int& nrows_out) {
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
-    float r[20];
+    float r[R][20];
 #pragma unroll
-    for (int q = 0; q < 20; q++) r[q] = -1.0f;
+    for (int s = 0; s < R; s++)
+#pragma unroll
+        for (int q = 0; q < 20; q++) r[s][q] = -1.0f;
     int nrows = 0;
-    const int cap = max_humans < 32 ? max_humans : 32;
+    const int cap = max_humans < 32 * R ? max_humans : 32 * R;
     bool fits = true;
 #pragma unroll
     for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
@@ -60,64 +64,107 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
         for (int k = 0; k < nc; k++) {
             const Conn cn = in.conn_at(limb, k);
             const float f1 = (float) cn.cid1, f2 = (float) cn.cid2;
-            const bool m = lane < nrows && (r[p1] == f1 || r[p2] == f2);
-            unsigned mask = __ballot_sync(FULL, m);
-            const int found = __popc(mask);
-            if (found == 1) {
-                if (m && r[p2] != f2) {
-                    r[p2] = f2;
-                    r[19] = __fadd_rn(r[19], 1.0f);
-                    r[18] = __fadd_rn(r[18], __fadd_rn(in.score_of(cn.cid2), cn.score));
-                }
-            } else if (found == 2) {
-                const int s1 = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int s2 = __ffs(mask) - 1;
-                bool both = false;
-                float o[20];
+            // row search (pafprocess.cpp:137-144): first two matches in row order, and the count
+            int found = 0, s1 = 0, s2 = 0;
+            bool m[R];
 #pragma unroll
-                for (int q = 0; q < 20; q++) o[q] = __shfl_sync(FULL, r[q], s2);
-#pragma unroll
-                for (int q = 0; q < 18; q++) both |= (r[q] > 0.f && o[q] > 0.f);
-                const bool membership = __shfl_sync(FULL, (int) both, s1) != 0;
-                if (!membership) {
-                    if (lane == s1) {
-#pragma unroll
-                        for (int q = 0; q < 18; q++) r[q] = __fadd_rn(r[q], __fadd_rn(o[q], 1.0f));
-                        r[19] = __fadd_rn(r[19], o[19]);
-                        r[18] = __fadd_rn(__fadd_rn(r[18], o[18]), cn.score);
+            for (int s = 0; s < R; s++) {
+                m[s] = (32 * s + lane) < nrows && (r[s][p1] == f1 || r[s][p2] == f2);
+                unsigned mask = __ballot_sync(FULL, m[s]);
+                const int c = __popc(mask);
+                if (c) {
+                    if (found == 0) {
+                        s1 = 32 * s + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (mask) s2 = 32 * s + __ffs(mask) - 1;
+                    } else if (found == 1) {
+                        s2 = 32 * s + __ffs(mask) - 1;
                     }
+                    found += c;
+                }
+            }
+            if (found == 1) {
 #pragma unroll
-                    for (int q = 0; q < 20; q++) {  // erase row s2: rows above it move down one lane
-                        const float nx = __shfl_down_sync(FULL, r[q], 1);
-                        if (lane >= s2) r[q] = nx;
+                for (int s = 0; s < R; s++)
+                    if (m[s] && r[s][p2] != f2) {
+                        r[s][p2] = f2;
+                        r[s][19] = __fadd_rn(r[s][19], 1.0f);
+                        r[s][18] = __fadd_rn(r[s][18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                    }
+            } else if (found == 2) {
+                const int l1 = s1 & 31, l2 = s2 & 31, t1 = s1 >> 5, t2 = s2 >> 5;
+                float o[20], mine[20];  // row s2 broadcast to every lane; lane l1's own copy of row s1
+#pragma unroll
+                for (int q = 0; q < 20; q++) {
+                    float v2 = r[0][q], v1 = r[0][q];
+#pragma unroll
+                    for (int s = 1; s < R; s++) {
+                        if (t2 == s) v2 = r[s][q];
+                        if (t1 == s) v1 = r[s][q];
+                    }
+                    o[q] = __shfl_sync(FULL, v2, l2);
+                    mine[q] = v1;
+                }
+                bool both = false;
+#pragma unroll
+                for (int q = 0; q < 18; q++) both |= (mine[q] > 0.f && o[q] > 0.f);
+                const bool membership = __shfl_sync(FULL, (int) both, l1) != 0;
+                if (!membership) {
+#pragma unroll
+                    for (int s = 0; s < R; s++)
+                        if (lane == l1 && t1 == s) {
+#pragma unroll
+                            for (int q = 0; q < 18; q++) r[s][q] = __fadd_rn(r[s][q], __fadd_rn(o[q], 1.0f));
+                            r[s][19] = __fadd_rn(r[s][19], o[19]);
+                            r[s][18] = __fadd_rn(__fadd_rn(r[s][18], o[18]), cn.score);
+                        }
+                    // erase row s2: every row above it moves down by one index
+#pragma unroll
+                    for (int q = 0; q < 20; q++) {
+                        float head[R];  // lane 0's value of each slot (what lane 31 of the slot below inherits)
+#pragma unroll
+                        for (int s = 0; s < R; s++) head[s] = __shfl_sync(FULL, r[s][q], 0);
+#pragma unroll
+                        for (int s = 0; s < R; s++) {
+                            float nx = __shfl_down_sync(FULL, r[s][q], 1);
+                            if (lane == 31) nx = (s + 1 < R) ? head[s + 1 < R ? s + 1 : s] : r[s][q];
+                            if (32 * s + lane >= s2) r[s][q] = nx;
+                        }
                     }
                     nrows--;
-                } else if (lane == s1) {
-                    r[p2] = f2;
-                    r[19] = __fadd_rn(r[19], 1.0f);
-                    r[18] = __fadd_rn(r[18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                } else {
+#pragma unroll
+                    for (int s = 0; s < R; s++)
+                        if (lane == l1 && t1 == s) {
+                            r[s][p2] = f2;
+                            r[s][19] = __fadd_rn(r[s][19], 1.0f);
+                            r[s][18] = __fadd_rn(r[s][18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                        }
                 }
             } else if (found == 0 && limb < 18) {
                 if (nrows >= cap) { fits = false; break; }
-                if (lane == nrows) {
 #pragma unroll
-                    for (int q = 0; q < 18; q++) r[q] = -1.0f;
-                    r[p1] = f1;
-                    r[p2] = f2;
-                    r[19] = 2.0f;
-                    r[18] = __fadd_rn(__fadd_rn(in.score_of(cn.cid1), in.score_of(cn.cid2)), cn.score);
-                }
+                for (int s = 0; s < R; s++)
+                    if (32 * s + lane == nrows) {
+#pragma unroll
+                        for (int q = 0; q < 18; q++) r[s][q] = -1.0f;
+                        r[s][p1] = f1;
+                        r[s][p2] = f2;
+                        r[s][19] = 2.0f;
+                        r[s][18] = __fadd_rn(__fadd_rn(in.score_of(cn.cid1), in.score_of(cn.cid2)), cn.score);
+                    }
                 nrows++;
             }
         }
         if (!fits) break;
     }
     if (!fits) return false;
-    if (lane < nrows) {
 #pragma unroll
-        for (int q = 0; q < 20; q++) rows_out[lane * 20 + q] = r[q];
-    }
+    for (int s = 0; s < R; s++)
+        if (32 * s + lane < nrows) {
+#pragma unroll
+            for (int q = 0; q < 20; q++) rows_out[(32 * s + lane) * 20 + q] = r[s][q];
+        }
     nrows_out = nrows;
     __syncwarp();
     return true;
@@ -249,7 +296,16 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     // ---- sequential assembly ------------------------------------------------------------------
     int nrows = 0;
     bool ovf = false;
-    if (!assemble_in_registers(in, max_humans, rows, nrows)) assemble_in_smem(in, max_humans, rows, nrows, ovf);
+    // People per image ~ the largest per-limb connection count; pick the register capacity from it
+    // (32, 64 or 128 rows) and fall back to the next larger one, finally to shared memory.
+    int max_conn = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_conn = max(max_conn, __shfl_xor_sync(0xffffffffu, max_conn, o));
+    bool done = false;
+    if (max_conn <= 24) done = assemble_in_registers<1>(in, max_humans, rows, nrows);
+    if (!done && max_conn <= 56 && max_humans > 32) done = assemble_in_registers<2>(in, max_humans, rows, nrows);
+    if (!done && max_conn <= 120 && max_humans > 64) done = assemble_in_registers<4>(in, max_humans, rows, nrows);
+    if (!done) assemble_in_smem(in, max_humans, rows, nrows, ovf);
     __syncwarp();
 
     // ---- prune (pafprocess.cpp:187-191: a reverse erase loop == an order-preserving filter) and
