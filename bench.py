@@ -320,6 +320,27 @@ def run_ours(args, rank, local_rank, world):
     iso_ms, _ = pp.stage_times()
     pp.set_timing(False)
 
+    # ---- context numbers (not the headline): the same batch without materialising the operator-surface
+    #      tensors, and through the reference's own front-end (stride-8 NMS + bicubic refinement)
+    def variant(frontend, materialize, steps=100):
+        for i in range(4):
+            pps[i % 2].run(*sets_dev[i % INPUT_SETS], layout="nchw", frontend=frontend, materialize=materialize, stream=streams[i % 2])
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for s_ in streams:
+            s_.wait_stream(stream)
+        for i in range(steps):
+            pps[i % 2].run(*sets_dev[i % INPUT_SETS], layout="nchw", frontend=frontend, materialize=materialize, stream=streams[i % 2])
+        for s_ in streams:
+            stream.wait_stream(s_)
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        return BATCH * steps / (a.elapsed_time(b) / 1000.0)
+
+    variants = {"dense_frontend_no_materialise_images_per_s": variant("dense", False),
+                "reference_frontend_no_materialise_images_per_s": variant("reference", False)}
+
     # ---- e2e: host buffers through the C ABI, copies in the timed region ---------------------------
     # A stream of batches the way a caller would drive it: two contexts on two streams, so the H2D
     # copy of batch i+1 overlaps the kernels of batch i; EVERY step's inputs come from pinned host
@@ -398,6 +419,7 @@ def run_ours(args, rank, local_rank, world):
                     "api": "ekp_postprocess_host + ekp_results_humans (pinned host buffers; 2 contexts / 2 streams "
                            "so the H2D of one batch overlaps the kernels of the previous one)"},
             "gpu_launches": int(launches), "clocks": clk, "humans_found_last_step": total_humans,
+            "variants_per_gpu": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
             import oracle

@@ -365,3 +365,26 @@ def test_assembly_paths_by_people_count(ek, people):
     assert len(sub) == people == int(res["num_humans"][0])
     assert_bits_equal(res["subset"][0, :people], sub, "subset")
     big.close()
+
+
+def test_batched_handoff_from_the_network(ek):
+    """Row f1: a (fake) network emits CUDA tensors for a batch of frames; infer_humans must give the
+    people paf_to_pose_cpp gives frame by frame on host copies."""
+    from torch_ekpose_b200 import estimator, synthetic
+    heat, paf = synthetic.make_batch(3, 46, 54, (2, 4), seed=21)
+
+    class FakeNet(torch.nn.Module):
+        def forward(self, x):
+            # get_outputs scales the LONG side to 368 (estimator.py:59,73): 368x432 -> 313x368 -> padded 320x368
+            assert x.shape == (3, 3, 320, 368) and x.is_cuda
+            return (torch.from_numpy(paf).to(x.device), torch.from_numpy(heat).to(x.device)), None
+
+    frames = [np.zeros((368, 432, 3), np.uint8) for _ in range(3)]
+    got = estimator.infer_humans(frames, FakeNet(), "vgg", torch.device("cuda", 0))
+    for i in range(3):
+        want = ek.paf_to_pose_cpp(heat[i].transpose(1, 2, 0), paf[i].transpose(1, 2, 0), ek.cfg)
+        assert len(got[i]) == len(want) > 0
+        for a, b in zip(got[i], want):
+            assert a.score == b.score and sorted(a.body_parts) == sorted(b.body_parts)
+            assert all((a.body_parts[k].x, a.body_parts[k].y, a.body_parts[k].score) ==
+                       (b.body_parts[k].x, b.body_parts[k].y, b.body_parts[k].score) for k in a.body_parts)

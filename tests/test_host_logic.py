@@ -90,3 +90,24 @@ def test_coco_conversion_vectorised_equals_object_path():
         assert a["image_id"] == b["image_id"] and a["category_id"] == 1 and a["score"] == 1.0
         assert len(a["keypoints"]) == 51 and a["keypoints"] == b["keypoints"]
     assert coco.ORDER_COCO == [0, 15, 14, 17, 16, 5, 2, 6, 3, 7, 4, 11, 8, 12, 9, 13, 10]
+
+
+def test_estimator_geometry_matches_reference_helpers():
+    """padding / preprocessing of the batched hand-off keep the reference's geometry (estimator.py:52-68)."""
+    cv2 = pytest.importorskip("cv2")
+    from torch_ekpose_b200 import estimator
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    pad, scale, shp = estimator.padding(img, 368)
+    assert scale == 368 / 640 and pad.shape == (280, 368, 3) and shp == (276, 368, 3)
+    assert not pad[276:].any()
+    x = estimator.vgg_preprocess(pad)
+    assert x.shape == (3, 280, 368) and x.dtype == np.float32
+    want_r = (np.float32(pad[10, 20, 2]) / np.float32(255.) - np.float32(0.485)) / np.float32(0.229)
+    assert abs(x[0, 10, 20] - want_r) < 1e-6
+    import os, sys
+    if os.path.isdir("/root/reference"):   # and bit-for-bit against the reference's own functions
+        sys.path.insert(0, "/root/reference")
+        from lib.datasets import preprocessing as ref_prep
+        assert np.array_equal(ref_prep.vgg_preprocess(pad), x)
+        assert np.array_equal(ref_prep.rtpose_preprocess(pad), estimator.rtpose_preprocess(pad))
