@@ -230,40 +230,59 @@ __device__ __forceinline__ void nms_row(NmsState& st, float S, int X, int Y, boo
     st.s1 = S;
 }
 
-template <bool kMat, bool kDebug>
-__global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kernel(const DenseParams p) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(16) float sTaps[64];  // interior taps by phase (copy of cTapsInterior for per-lane indexing)
-    __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];  // (part, strip) tasks that survive the early-out
-    __shared__ int sNumActive;
-    if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
-    if (threadIdx.x == 0) sNumActive = 0;
-    const int img = blockIdx.z;
-    const int m0 = blockIdx.y * kTB;
-    const int i0 = blockIdx.x * p.tile_wl;
-    const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
-    const int twl = min(p.tile_wl, w - i0);
-    const int tb = min(kTB, h - m0);
-    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
+// ---- one tile ------------------------------------------------------------------------------------
+struct TileGeom {
+    int img, m0, i0, twl, tb;
+    int hr0, hr1, hc0, hc1;  // staged heat rows / columns (smoothing window +-3 cells, clamped like the taps)
+    int pr0, pr1, pc0, pc1;  // staged PAF rows / columns (bilinear row pairs of the tile)
+};
 
-    float* sHeat = smem;                                    // [kHeatRows][hcols][19]
-    float* sPaf = sHeat + kHeatRows * hcols * EKP_HEAT_CH;  // [kPafRows][pcols][38]
-    float* sColMax = sPaf + kPafRows * pcols * EKP_PAF_CH;  // [hcols][19] max(0, column maximum over the staged rows)
-
+__device__ __forceinline__ TileGeom tile_geom(const DenseParams& p, int tile_x, int tile_y, int img) {
+    TileGeom g;
+    const int h = p.h, w = p.w;
+    g.img = img;
+    g.m0 = tile_y * kTB;
+    g.i0 = tile_x * p.tile_wl;
+    g.twl = min(p.tile_wl, w - g.i0);
+    g.tb = min(kTB, h - g.m0);
     // the smoothing window of row block m is rows clamp(m-2, 0, h-5) .. +4 (same for columns)
-    const int hr0 = max(min(m0 - 3, h - 5), 0), hr1 = min(max(m0 + tb + 2, 4), h - 1);
-    const int hc0 = max(min(i0 - 3, w - 5), 0), hc1 = min(max(i0 + twl + 2, 4), w - 1);
-    const int pr0 = max(m0 - 1, 0), pr1 = min(m0 + tb - 1, h - 1);
-    const int pc0 = max(i0 - 1, 0), pc1 = min(i0 + twl, w - 1);
+    g.hr0 = max(min(g.m0 - 3, h - 5), 0); g.hr1 = min(max(g.m0 + g.tb + 2, 4), h - 1);
+    g.hc0 = max(min(g.i0 - 3, w - 5), 0); g.hc1 = min(max(g.i0 + g.twl + 2, 4), w - 1);
+    g.pr0 = max(g.m0 - 1, 0); g.pr1 = min(g.m0 + g.tb - 1, h - 1);
+    g.pc0 = max(g.i0 - 1, 0); g.pc1 = min(g.i0 + g.twl, w - 1);
+    return g;
+}
 
-    // The PAF patch (2/3 of the stores depend on it) is requested first and the heat patch second,
-    // as two cp.async groups: paf_mat is streamed out while the heat patch is still in flight.
+struct TileSmem {
+    float* heat;    // [kHeatRows][tile_wl + 6][19]
+    float* paf;     // [kPafRows][tile_wl + 2][38]
+};
+
+// Request a tile's stride-8 patches.  The PAF patch (2/3 of the stores depend on it) goes first and
+// the heat patch second, as two cp.async groups.
+template <bool kMat>
+__device__ __forceinline__ void issue_stage(const DenseParams& p, const TileGeom& g, const TileSmem& sm) {
+    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
     if (kMat) {
-        stage_patch<EKP_PAF_CH>(sPaf, p.paf, p.layout, img, h, w, pr0, pr1, pc0, pc1, pcols);
+        stage_patch<EKP_PAF_CH>(sm.paf, p.paf, p.layout, g.img, p.h, p.w, g.pr0, g.pr1, g.pc0, g.pc1, pcols);
         stage_commit();
     }
-    stage_patch<EKP_HEAT_CH>(sHeat, p.heat, p.layout, img, h, w, hr0, hr1, hc0, hc1, hcols);
+    stage_patch<EKP_HEAT_CH>(sm.heat, p.heat, p.layout, g.img, p.h, p.w, g.hr0, g.hr1, g.hc0, g.hc1, hcols);
     stage_commit();
+}
+
+// Everything after the patches were requested (they are the two most recent cp.async groups):
+// paf_mat is streamed out while the heat patch is still in flight.
+template <bool kMat, bool kDebug>
+__device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeom& g, const TileSmem& sm, float* sColMax,
+                                             const float* sTaps, unsigned short* sList, int* sNumActive) {
+    const int img = g.img, m0 = g.m0, i0 = g.i0, twl = g.twl, tb = g.tb;
+    const int hr0 = g.hr0, hr1 = g.hr1, hc0 = g.hc0, hc1 = g.hc1, pr0 = g.pr0, pc0 = g.pc0;
+    const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
+    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
+    float* sHeat = sm.heat;
+    float* sPaf = sm.paf;
+
     if (kMat) {
         stage_wait<1>();
         __syncthreads();
@@ -315,10 +334,10 @@ __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kerne
             for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, sColMax[(i - hc0) * EKP_HEAT_CH + c]);
             active = mx > p.thr * 0.99999f;
         }
-        if (active) sList[atomicAdd(&sNumActive, 1)] = (unsigned short) t;
+        if (active) sList[atomicAdd(sNumActive, 1)] = (unsigned short) t;
     }
     __syncthreads();
-    const int nactive = sNumActive;
+    const int nactive = *sNumActive;
 
     for (int li = warp; li < nactive; li += kThreads / 32) {
         const int task = sList[li];
@@ -417,11 +436,28 @@ __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kerne
     }
 }
 
+template <bool kMat, bool kDebug>
+__global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kernel(const DenseParams p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) float sTaps[64];  // interior taps by phase (copy of cTapsInterior for per-lane indexing)
+    __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];  // (part, strip) tasks that survive the early-out
+    __shared__ int sNumActive;
+    if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
+    if (threadIdx.x == 0) sNumActive = 0;
+    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
+    TileSmem sm;
+    sm.heat = smem;
+    sm.paf = sm.heat + kHeatRows * hcols * EKP_HEAT_CH;
+    float* sColMax = sm.paf + kPafRows * pcols * EKP_PAF_CH;  // [hcols][19] max(0, column maximum over the staged rows)
+    const TileGeom g = tile_geom(p, blockIdx.x, blockIdx.y, blockIdx.z);
+    issue_stage<kMat>(p, g, sm);
+    process_tile<kMat, kDebug>(p, g, sm, sColMax, sTaps, sList, &sNumActive);
+}
+
 size_t dense_frontend_smem_bytes(int tile_wl) {
     return sizeof(float) * ((size_t) kHeatRows * (tile_wl + 6) * EKP_HEAT_CH + (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH +
                             (size_t) (tile_wl + 6) * EKP_HEAT_CH);
 }
-
 // choose the stride-8 tile width: <= kMaxTwl columns, tiles of (nearly) equal width
 int dense_frontend_tile_wl(int w) {
     const int nt = (w + kMaxTwl - 1) / kMaxTwl;
@@ -437,6 +473,9 @@ cudaError_t configure_dense_frontend() {
     return e;
 }
 
+// One CTA per tile.  (A persistent variant -- resident CTAs pulling tiles from a counter with the
+// next tile's patches prefetched into a double buffer -- was measured 7 % SLOWER on B200, 0.442 vs
+// 0.412 ms: it loses the PAF-first overlap and runs the CTAs in lock-step; see profiles/README.md.)
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
     const size_t smem = dense_frontend_smem_bytes(p.tile_wl);
     dim3 grid((p.w + p.tile_wl - 1) / p.tile_wl, (p.h + kTB - 1) / kTB, p.n);
