@@ -388,3 +388,40 @@ def test_batched_handoff_from_the_network(ek):
             assert a.score == b.score and sorted(a.body_parts) == sorted(b.body_parts)
             assert all((a.body_parts[k].x, a.body_parts[k].y, a.body_parts[k].score) ==
                        (b.body_parts[k].x, b.body_parts[k].y, b.body_parts[k].score) for k in a.body_parts)
+
+
+def test_random_shapes_layouts_thresholds_vs_oracle(ek):
+    """Fuzz: random map sizes (incl. odd / tiny / wide), layouts, thresholds, random fields instead of
+    person-like scenes; both front-ends; peaks and people must equal the oracle bit for bit."""
+    rng = np.random.default_rng(2024)
+    pp = ek.PostProcessor(device=0, max_batch=3, max_h=48, max_w=80, max_peaks=8192, max_humans=512)
+    fe = util.frontend()
+    for trial in range(12):
+        h, w = int(rng.integers(5, 48)), int(rng.integers(5, 80))
+        n = int(rng.integers(1, 4))
+        layout = "nchw" if trial % 2 else "nhwc"
+        thr = float(rng.choice([0.22, 0.3, 0.6]))
+        # a random background below every threshold plus a few sharp spikes (so that peaks stay sparse)
+        heat = rng.random((n, h, w, 19)).astype(np.float32) * 0.2
+        for _ in range(int(rng.integers(0, 60))):
+            heat[rng.integers(0, n), rng.integers(0, h), rng.integers(0, w), rng.integers(0, 18)] = rng.random() * 0.9 + 0.2
+        paf = rng.normal(0, 0.5, (n, h, w, 38)).astype(np.float32)
+        hin = heat if layout == "nhwc" else np.ascontiguousarray(heat.transpose(0, 3, 1, 2))
+        pin = paf if layout == "nhwc" else np.ascontiguousarray(paf.transpose(0, 3, 1, 2))
+        for frontend in ("dense", "reference"):
+            pp.run(_dev(hin), _dev(pin), layout=layout, frontend=frontend, thr=thr, materialize=bool(trial % 3 == 0))
+            res = pp.results(with_peaks=True)
+            assert not res["overflow"].any(), (trial, frontend)
+            for i in range(n):
+                if frontend == "dense":
+                    peaks = fe.dense_nms(fe.dense_smooth(heat[i]), np.float32(thr))
+                    paf_mat = fe.upsample_bilinear(paf[i])
+                else:
+                    peaks = fe.ref_nms(heat[i], np.float32(thr))
+                    paf_mat = fe.upsample_nearest(paf[i])
+                assert_bits_equal(util.peaks_table(res, i), peaks, f"trial {trial} {frontend} {h}x{w} {layout} image {i} peaks")
+                sub, _ = util.oracle_people(peaks, 8 * h, 8 * w, paf_mat)
+                m = int(res["num_humans"][i])
+                assert m == len(sub), (trial, frontend, i, m, len(sub))
+                assert_bits_equal(res["subset"][i, :m], sub, f"trial {trial} {frontend} image {i} subset")
+    pp.close()

@@ -44,6 +44,10 @@ constexpr int kRowBatch = EKP_ROW_BATCH;  // output rows whose stores are kept i
 constexpr int kThreads = EKP_THREADS;
 constexpr int kMaxTwl = EKP_MAX_TWL;      // widest tile in stride-8 columns
 constexpr unsigned kPrefetchCtas = 148u * EKP_MIN_BLOCKS;  // one resident wave on a B200
+#ifndef EKP_NMS_WARPS
+#define EKP_NMS_WARPS 2
+#endif
+constexpr int kNmsWarps = EKP_NMS_WARPS;  // warps that start on NMS strips rather than heat_mat chunks
 constexpr int kTH = 16;             // full-resolution rows per tile
 constexpr int kTB = kTH / 8;        // stride-8 row blocks per tile
 constexpr int kHeatRows = kTB + 6;  // stride-8 rows staged for the smoothing window
@@ -103,16 +107,18 @@ __device__ __forceinline__ void stage_patch(float* __restrict__ sP, const float*
 // Every thread owns float4 columns of the tile's output rows: 4 consecutive (x, c) entries, for
 // which the horizontal interpolation is done once per stride-8 row and each output row costs
 // four FMAs and one 16-byte store.
+// Columns col_begin, col_begin + col_step, ... of the tile row are handled by the calling thread (the
+// whole block strides by kThreads; a single warp takes one 32-column chunk).
 template <int C>
 __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, int pr0, int pc0, int pcols,
                                                  float* __restrict__ out_img, int h, int w, int m0, int tb,
-                                                 int i0, int twl) {
+                                                 int i0, int twl, int col_begin, int col_step) {
     const int W = w * 8;
     const int X0 = i0 * 8;
     const int row_f4 = twl * 2 * C;  // (8*twl*C)/4 float4 per tile row
     const size_t stride4 = (size_t) W * C / 4;
     const int prow = pcols * C;
-    for (int col = threadIdx.x; col < row_f4; col += kThreads) {
+    for (int col = col_begin; col < row_f4; col += col_step) {
         int off0[4], off1[4];
         float tx[4];
 #pragma unroll
@@ -276,7 +282,8 @@ __device__ __forceinline__ void issue_stage(const DenseParams& p, const TileGeom
 // paf_mat is streamed out while the heat patch is still in flight.
 template <bool kMat, bool kDebug>
 __device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeom& g, const TileSmem& sm, float* sColMax,
-                                             const float* sTaps, unsigned short* sList, int* sNumActive) {
+                                             const float* sTaps, unsigned short* sList, int* sNumActive, int* sNextTask,
+                                             int* sNextChunk) {
     const int img = g.img, m0 = g.m0, i0 = g.i0, twl = g.twl, tb = g.tb;
     const int hr0 = g.hr0, hr1 = g.hr1, hc0 = g.hc0, hc1 = g.hc1, pr0 = g.pr0, pc0 = g.pc0;
     const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
@@ -287,7 +294,8 @@ __device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeo
     if (kMat) {
         stage_wait<1>();
         __syncthreads();
-        materialise_tile<EKP_PAF_CH>(sPaf, pr0, pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0, twl);
+        materialise_tile<EKP_PAF_CH>(sPaf, pr0, pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0, twl,
+                                      threadIdx.x, kThreads);
     }
     stage_wait<0>();
     __syncthreads();
@@ -299,8 +307,6 @@ __device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeo
             sColMax[idx] = mx;
         }
     }
-    if (kMat && p.heat_mat)
-        materialise_tile<EKP_HEAT_CH>(sHeat, hr0, hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0, tb, i0, twl);
     if (!kDebug) __syncthreads();  // sColMax complete
 
     const int lane = threadIdx.x & 31;
@@ -340,8 +346,35 @@ __device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeo
     __syncthreads();
     const int nactive = *sNumActive;
 
-    for (int li = warp; li < nactive; li += kThreads / 32) {
-        const int task = sList[li];
+    // ---- heat_mat chunks and surviving NMS strips share the warps dynamically ---------------------
+    // Two warps start on the (ALU-bound) NMS strips, the others on the (store-bound) 32-column chunks
+    // of heat_mat; whoever runs out of its own kind takes the other.  Stores thus keep flowing while
+    // the smoothing runs, and heavy tiles (many people) are balanced across all warps.
+    const int nchunks = (kMat && p.heat_mat) ? (twl * 2 * EKP_HEAT_CH + 31) / 32 : 0;
+    const bool nms_first = warp < kNmsWarps;
+    for (;;) {
+        int kind = -1, item = 0;
+        if (lane == 0) {
+            if (nms_first) {
+                item = atomicAdd(sNextTask, 1);
+                if (item < nactive) kind = 0;
+                else { item = atomicAdd(sNextChunk, 1); if (item < nchunks) kind = 1; }
+            } else {
+                item = atomicAdd(sNextChunk, 1);
+                if (item < nchunks) kind = 1;
+                else { item = atomicAdd(sNextTask, 1); if (item < nactive) kind = 0; }
+            }
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (kind < 0) break;
+        if (kind == 1) {
+            if (kMat)
+                materialise_tile<EKP_HEAT_CH>(sHeat, hr0, hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0, tb, i0,
+                                              twl, item * 32 + lane, 1 << 30);
+            continue;
+        }
+        const int task = sList[item];
         const int c = (int) fastdiv(task, m_strips);
         const int strip = task - c * nstrips;
         const int X = X0 - 1 + 30 * strip + lane;
@@ -442,9 +475,9 @@ __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kerne
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) float sTaps[64];  // interior taps by phase (copy of cTapsInterior for per-lane indexing)
     __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];  // (part, strip) tasks that survive the early-out
-    __shared__ int sNumActive;
+    __shared__ int sNumActive, sNextTask, sNextChunk;
     if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
-    if (threadIdx.x == 0) sNumActive = 0;
+    if (threadIdx.x == 0) { sNumActive = 0; sNextTask = 0; sNextChunk = 0; }
     const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
     TileSmem sm;
     sm.heat = smem;
@@ -468,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kerne
         }
     }
     issue_stage<kMat>(p, g, sm);
-    process_tile<kMat, kDebug>(p, g, sm, sColMax, sTaps, sList, &sNumActive);
+    process_tile<kMat, kDebug>(p, g, sm, sColMax, sTaps, sList, &sNumActive, &sNextTask, &sNextChunk);
 }
 
 size_t dense_frontend_smem_bytes(int tile_wl) {
