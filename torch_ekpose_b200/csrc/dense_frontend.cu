@@ -1,27 +1,37 @@
 // dense_frontend.cu -- stages 1-3 of the hot path, fused, for sm_100a.
 //
 // One launch takes the network's stride-8 heat (19 ch) and PAF (38 ch) maps of a whole batch
-// and, per 16-row x (8*tile_wl)-column full-resolution tile,
-//   (1) stages the stride-8 neighbourhood of the tile in shared memory (HWC order),
+// and, per 16-row x (8*tile_wl)-column full-resolution tile (one CTA of 256 threads, 3 CTAs/SM),
+//   (0) first wave of CTAs only: prefetches the whole batch's inputs into L2 (evict_last) in one
+//       burst, so input reads do not trickle in between the writes (HBM read/write turnarounds),
+//   (1) stages the stride-8 neighbourhood of the tile in shared memory (HWC order) with cp.async
+//       in two groups, PAF first,
 //   (2) optionally materialises the bilinear x8 tensors heat_mat[H][W][19] / paf_mat[H][W][38]
 //       (the operator-surface tensors of process_paf, paf_to_pose.py:356-360) with 16-byte
-//       coalesced streaming stores -- this is the HBM-bound part: 36.25 MB written per 368x432
-//       image against 0.57 MB read,
+//       coalesced streaming stores -- the HBM-bound part: 36.25 MB written per 368x432 image
+//       against 0.57 MB read; paf_mat is streamed out while the heat patch is still in flight,
 //   (3) evaluates the Gaussian-smoothed (sigma 3, 25 taps, reflect) bilinear-upsampled heat map
 //       as ONE separable 5-tap polyphase filter on the stride-8 grid (the composition of the two
-//       linear operators; tables built on the host in capi.cu) entirely in registers,
+//       linear operators; tables built on the host in capi.cu) entirely in registers -- only for
+//       the (part, 30-pixel strip) pairs that can contain a value above the threshold at all
+//       (exact early-out from a per-tile column-maximum table),
 //   (4) does the 3x3 max NMS with warp shuffles (x) and a rolling 3-row window (y) and appends
 //       peaks with a warp-ballot aggregated atomic into the per-image raw peak list.
-// Nothing but the (optional) operator-surface tensors and the peaks ever goes back to HBM.
+// heat_mat chunks and surviving NMS strips are handed out to the warps dynamically, so stores keep
+// flowing while the smoothing runs.  Nothing but the (optional) operator-surface tensors and the
+// peaks ever goes back to HBM.
 //
 // Arithmetic is the one defined in oracle/frontend_oracle.c part (B); results are bit-identical
 // to it (tests/test_gpu_parity.py).  There is no reference implementation of this front-end
 // (SURVEY.md 0.1); the reference's own front-end is ref_frontend.cu.
 //
-// The kernel is issue-slot bound before it is HBM bound (ncu, profiles/), so the inner loops are
-// written for instruction count: interior row blocks take their vertical taps from constant
-// memory as immediate operands, eight rows are unrolled so the rolling NMS state is renamed
-// instead of moved, and index decoding in the staging loops uses multiply-high division.
+// Why no TMA: cuTensorMap strides must be multiples of 16 bytes; the rows of these tensors are
+// 54 (or 82, 164) floats and the pixels 19 / 38 floats, so neither the NCHW nor the NHWC input
+// can be described by a tiled tensor map without re-padding it, and the NCHW -> HWC transpose
+// that the staging performs on the fly is not a box copy.  4-byte cp.async (LDGSTS) does both.
+//
+// The kernel started issue-slot bound (666 M warp instructions, 0.50 of the HBM roofline) and is
+// now store-stream bound (145 M, 0.92): see profiles/README.md for the ncu history and ablations.
 #include <type_traits>
 
 #include "common.cuh"
