@@ -9,10 +9,13 @@
 //  * roundpaf and criterion2 use the same two double-precision steps as the C++ source;
 //  * the ten sample scores are accumulated in sample order by the thread that owns the pair;
 //  * candidates are compacted in the reference's push order (a outer, b inner) with an ordered
-//    ballot/prefix compaction, then sorted by ONE thread with libstdc++'s std::sort algorithm
-//    (introsort: median-of-3 quicksort above 16 elements with heapsort fallback after
-//    2*floor(log2 n) levels, then insertion sort), because the reference's result depends on
-//    that algorithm's permutation of equal scores (pafprocess.cpp:97).
+//    ballot/prefix compaction;
+//  * sorting (pafprocess.cpp:97): the reference's result depends on HOW std::sort permutes equal
+//    scores.  For n <= 16 libstdc++ runs a stable insertion sort, and without ties the order is
+//    unique, so all threads rank the candidates in parallel (stable) and look for ties; only when
+//    n > 16 AND ties exist does one thread replay libstdc++'s algorithm on the original sequence
+//    (introsort: median-of-3 quicksort above 16 elements, heapsort after 2*floor(log2 n) levels,
+//    then the final insertion sort), which reproduces the reference's permutation exactly.
 #include "common.cuh"
 
 namespace ekp {
