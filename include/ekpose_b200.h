@@ -131,6 +131,17 @@ int ekp_results_parts(ekp_ctx *ctx, int *part_off);
 int ekp_dense_smooth_debug(ekp_ctx *ctx, const float *heat, int n, int h, int w, int layout, float *smooth_out,
                            void *stream);
 
+/* ---- input side --------------------------------------------------------
+ * Geometry of the reference's `padding` (lib/evaluate/estimator.py:52-68): the long side is scaled
+ * to dest_size (cv2.resize, INTER_LINEAR), then zero-padded to a multiple of `factor`. */
+int ekp_preprocess_dims(int src_h, int src_w, int dest_size, int factor, int *resized_h, int *resized_w,
+                        int *padded_h, int *padded_w, double *scale);
+/* padding + vgg_preprocess (mode 0) / rtpose_preprocess (mode 1) (lib/datasets/preprocessing.py:16-43)
+ * for n equally sized uint8 BGR frames [n, src_h, src_w, 3] (DEVICE) -> float32 [n, 3, padded_h,
+ * padded_w] (DEVICE), bit-identical to the reference's Python. */
+int ekp_preprocess(ekp_ctx *ctx, const unsigned char *frames, int n, int src_h, int src_w, int dest_size,
+                   int factor, int mode, float *out, void *stream);
+
 /* Per-stage device timing for the benchmark.  When enabled, CUDA events are recorded on the work
  * stream around each stage of every run (a ring of the last 64 runs).  ekp_stage_times waits for
  * the stream and returns the mean milliseconds of: [0] stages 1-3 (front-end kernel(s)),

@@ -190,6 +190,10 @@ class Frontend:
         L.okp_dense_smooth_sequential.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
         L.okp_dense_nms.restype = C.c_int
         L.okp_dense_nms.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_float, _f32p, C.c_int]
+        _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        L.okp_preprocess_dims.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_double)]
+        L.okp_resize_linear_u8.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _u8p]
+        L.okp_preprocess.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
 
     @staticmethod
     def _hwc(a):
@@ -248,6 +252,28 @@ class Frontend:
         n = self.lib.okp_dense_nms(smooth, smooth.shape[0], smooth.shape[1], smooth.shape[2], thr, out, cap)
         assert n <= cap
         return out[:n].copy()
+
+    def preprocess_dims(self, sh, sw, dest_size=368, factor=8):
+        v = [C.c_int() for _ in range(4)]
+        sc = C.c_double()
+        self.lib.okp_preprocess_dims(sh, sw, dest_size, factor, *[C.byref(x) for x in v], C.byref(sc))
+        return tuple(x.value for x in v) + (sc.value,)   # (rh, rw, ph, pw, scale)
+
+    def resize_linear_u8(self, img, scale) -> np.ndarray:
+        img = np.ascontiguousarray(img, np.uint8)
+        rh, rw, _, _, _ = self.preprocess_dims(img.shape[0], img.shape[1])
+        dh, dw = int(np.rint(img.shape[0] * scale)), int(np.rint(img.shape[1] * scale))
+        out = np.zeros((dh, dw, img.shape[2]), np.uint8)
+        self.lib.okp_resize_linear_u8(img, img.shape[0], img.shape[1], img.shape[2], scale, dh, dw, out)
+        return out
+
+    def preprocess(self, bgr, mode="vgg", dest_size=368, factor=8) -> np.ndarray:
+        """padding() + vgg_preprocess / rtpose_preprocess of one uint8 BGR image -> float32 [3, ph, pw]."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        _, _, ph, pw, _ = self.preprocess_dims(bgr.shape[0], bgr.shape[1], dest_size, factor)
+        out = np.zeros((3, ph, pw), np.float32)
+        self.lib.okp_preprocess(bgr, bgr.shape[0], bgr.shape[1], dest_size, factor, {"vgg": 0, "rtpose": 1}[mode], out)
+        return out
 
     def dense_peaks(self, heat, thr=0.15) -> np.ndarray:
         return self.dense_nms(self.dense_smooth(heat), thr)

@@ -425,3 +425,17 @@ def test_random_shapes_layouts_thresholds_vs_oracle(ek):
                 assert m == len(sub), (trial, frontend, i, m, len(sub))
                 assert_bits_equal(res["subset"][i, :m], sub, f"trial {trial} {frontend} image {i} subset")
     pp.close()
+
+
+@pytest.mark.parametrize("mode", ["vgg", "rtpose"])
+@pytest.mark.parametrize("shape", [(480, 640), (300, 500), (101, 77), (720, 1280)])
+def test_input_side_kernel_vs_oracle(pp, shape, mode):
+    """Row f4: padding + normalisation kernel == the oracle (== cv2 + the reference's Python) bit for bit."""
+    rng = np.random.default_rng(shape[0])
+    frames = rng.integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
+    out, scale = pp.preprocess(torch.from_numpy(frames).cuda(), mode=mode)
+    fe = util.frontend()
+    assert scale == fe.preprocess_dims(*shape)[4]
+    got = out.cpu().numpy()
+    for i in range(3):
+        assert_bits_equal(got[i], fe.preprocess(frames[i], mode), f"frame {i}")

@@ -113,3 +113,27 @@ def test_restatements_equal_reference_python_live():
             assert_bits_equal(sub, ref.subset(), "subset vs the reference run")
     finally:
         cv2.ipp.setUseIPP(was)
+
+
+def test_input_side_restatement_equals_cv2_and_reference_python():
+    """Row f4 oracle: padding() + vgg/rtpose_preprocess restated in C == cv2 (8-bit INTER_LINEAR is
+    OpenCV's own fixed-point code, no IPP for 8UC3) and == the reference's Python where it exists."""
+    cv2 = pytest.importorskip("cv2")
+    from torch_ekpose_b200 import estimator
+    fe = util.frontend()
+    rng = np.random.default_rng(1)
+    for (h, w) in [(480, 640), (720, 1280), (300, 500), (368, 432), (101, 77), (640, 480), (50, 50)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        rh, rw, ph, pw, scale = fe.preprocess_dims(h, w)
+        assert np.array_equal(fe.resize_linear_u8(img, scale), cv2.resize(img, None, fx=scale, fy=scale))
+        pad, s2, shp = estimator.padding(img, 368)
+        assert s2 == scale and pad.shape == (ph, pw, 3) and shp == (rh, rw, 3)
+        assert_bits_equal(fe.preprocess(img, "vgg"), estimator.vgg_preprocess(pad), "vgg")
+        assert_bits_equal(fe.preprocess(img, "rtpose"), estimator.rtpose_preprocess(pad), "rtpose")
+    if os.path.isdir(oracle.REF_ROOT):
+        import sys
+        sys.path.insert(0, oracle.REF_ROOT)
+        from lib.datasets import preprocessing as ref_prep
+        img = rng.integers(0, 256, (333, 555, 3), dtype=np.uint8)
+        pad, _, _ = estimator.padding(img, 368)
+        assert_bits_equal(fe.preprocess(img, "vgg"), ref_prep.vgg_preprocess(pad), "vs reference vgg_preprocess")

@@ -47,6 +47,8 @@ SIGNATURES = {
     "ekp_results_humans": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "ekp_results_parts": (_i, [_vp, _vp]),
     "ekp_dense_smooth_debug": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ekp_preprocess_dims": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ekp_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ekp_set_timing": (_i, [_vp, _i]),
     "ekp_stage_times": (_i, [_vp, _vp, _vp]),
     "ekp_max_batch": (_i, [_vp]),

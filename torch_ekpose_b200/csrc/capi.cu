@@ -34,6 +34,9 @@ cudaError_t configure_assemble(int max_humans, int max_peaks);
 cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,
                             int max_humans, int n, const unsigned* overflow, unsigned char* records, const ResultLayout& lay,
                             cudaStream_t stream);
+cudaError_t launch_preprocess(const unsigned char* src, float* out, const int* xofs, const short* ialpha, const int* yofs,
+                              const short* ibeta, int n, int sh, int sw, int rh, int rw, int ph, int pw, int mode,
+                              cudaStream_t stream);
 }  // namespace ekp
 
 using namespace ekp;
@@ -137,6 +140,8 @@ struct ekp_ctx {
     float* ay = nullptr;
     int tab_h = 0, tab_w = 0;
     float* cubic = nullptr;         // [8][4]
+    void* prep_tab = nullptr;       // resize tables of the input side for (prep_sh, prep_sw, prep_dest)
+    int prep_sh = 0, prep_sw = 0, prep_dest = 0, prep_rh = 0, prep_rw = 0;
     // pinned host mirrors of the results
     unsigned char* h_records = nullptr;
     ekp_peak* h_line = nullptr;
@@ -160,7 +165,7 @@ static int ctx_free(ekp_ctx* c) {
     if (!c) return EKP_OK;
     cudaSetDevice(c->device);
     void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->records,
-                   c->in_heat, c->in_paf, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic};
+                   c->in_heat, c->in_paf, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic, c->prep_tab};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {c->h_records, c->h_line};
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -429,6 +434,70 @@ extern "C" int ekp_results_humans(ekp_ctx* c, int* num_humans, ekp_peak* parts, 
         if (scores) memcpy(scores + (size_t) i * mh, rec + c->lay.off_hscore, sizeof(float) * (size_t) hd->num_humans);
     }
     return overflow_status(c);
+}
+
+// ---- input side ---------------------------------------------------------------------------------
+extern "C" int ekp_preprocess_dims(int sh, int sw, int dest_size, int factor, int* rh, int* rw, int* ph, int* pw, double* scale) {
+    if (sh < 1 || sw < 1 || dest_size < 1 || factor < 1) return fail(EKP_ERR_ARG, "ekp_preprocess_dims: bad arguments");
+    const int longest = sh > sw ? sh : sw;
+    const double sc = (double) ((float) dest_size) / (double) longest;  // float(dest_size) / im_size_max (estimator.py:59)
+    const int r_w = (int) lrint((double) sw * sc), r_h = (int) lrint((double) sh * sc);  // cv2: saturate_cast<int>(size * fx)
+    if (rh) *rh = r_h;
+    if (rw) *rw = r_w;
+    if (ph) *ph = (int) ceil((double) r_h / factor) * factor;
+    if (pw) *pw = (int) ceil((double) r_w / factor) * factor;
+    if (scale) *scale = sc;
+    return EKP_OK;
+}
+
+// OpenCV's 11-bit fixed-point bilinear coefficients (resize.cpp): the x axis zeroes the fraction at
+// the borders, the y axis keeps it and the kernel clamps the row indices instead.
+static void linear_table(int dn, int sn, double scale, bool clamp_frac, int* ofs, short* coef) {
+    for (int d = 0; d < dn; d++) {
+        volatile float f = (float) (((double) d + 0.5) * scale - 0.5);
+        int s = (int) floorf(f);
+        f = f - (float) s;
+        if (clamp_frac && s < 0) { f = 0.f; s = 0; }
+        if (clamp_frac && s >= sn - 1) { f = 0.f; s = sn - 1; }
+        ofs[d] = s;
+        volatile float w0 = (1.f - f) * 2048.f, w1 = f * 2048.f;
+        coef[2 * d] = (short) lrint((double) w0);
+        coef[2 * d + 1] = (short) lrint((double) w1);
+    }
+}
+
+extern "C" int ekp_preprocess(ekp_ctx* c, const unsigned char* frames, int n, int sh, int sw, int dest_size, int factor,
+                              int mode, float* out, void* stream) {
+    if (!c) return fail(EKP_ERR_ARG, "ekp_preprocess: NULL context");
+    if (!frames || !out || n < 1 || (mode != 0 && mode != 1)) return fail(EKP_ERR_ARG, "ekp_preprocess: bad arguments");
+    int rh, rw, ph, pw;
+    double scale;
+    int rc = ekp_preprocess_dims(sh, sw, dest_size, factor, &rh, &rw, &ph, &pw, &scale);
+    if (rc) return rc;
+    if (rh < 1 || rw < 1) return fail(EKP_ERR_ARG, "ekp_preprocess: image too small");
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(c->device));
+    const size_t tab_bytes = sizeof(int) * ((size_t) rw + rh) + sizeof(short) * 2 * ((size_t) rw + rh);
+    if (c->prep_sh != sh || c->prep_sw != sw || c->prep_dest != dest_size) {
+        std::vector<int> ofs((size_t) rw + rh);
+        std::vector<short> coef(2 * ((size_t) rw + rh));
+        linear_table(rw, sw, 1.0 / scale, true, ofs.data(), coef.data());
+        linear_table(rh, sh, 1.0 / scale, false, ofs.data() + rw, coef.data() + 2 * (size_t) rw);
+        CU(cudaStreamSynchronize(st));
+        if (c->prep_tab) { cudaFree(c->prep_tab); c->prep_tab = nullptr; }
+        c->prep_sh = c->prep_sw = 0;
+        CU(cudaMalloc(&c->prep_tab, tab_bytes));
+        CU(cudaMemcpy(c->prep_tab, ofs.data(), sizeof(int) * ofs.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((char*) c->prep_tab + sizeof(int) * ofs.size(), coef.data(), sizeof(short) * coef.size(), cudaMemcpyHostToDevice));
+        c->prep_sh = sh; c->prep_sw = sw; c->prep_dest = dest_size; c->prep_rh = rh; c->prep_rw = rw;
+    }
+    const int* xofs = (const int*) c->prep_tab;
+    const int* yofs = xofs + rw;
+    const short* ialpha = (const short*) ((const char*) c->prep_tab + sizeof(int) * ((size_t) rw + rh));
+    const short* ibeta = ialpha + 2 * (size_t) rw;
+    CU(launch_preprocess(frames, out, xofs, ialpha, yofs, ibeta, n, sh, sw, rh, rw, ph, pw, mode, st));
+    c->launches += 1;
+    return EKP_OK;
 }
 
 extern "C" int ekp_set_timing(ekp_ctx* c, int enable) {

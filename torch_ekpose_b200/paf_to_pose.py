@@ -215,6 +215,23 @@ class PostProcessor:
         _lib.check(_lib.lib.ekp_stage_times(self._ctx, ms, C.byref(runs)))
         return dict(frontend=ms[0], peak_sort=ms[1], connect=ms[2], assemble=ms[3]), runs.value
 
+    def preprocess(self, frames, mode: str = "vgg", dest_size: int = 368, factor: int = 8, stream=None):
+        """Input side (row f4): uint8 BGR frames [n, H, W, 3] as a CUDA tensor -> the network input
+        float32 [n, 3, padded_h, padded_w] on the same device, bit-identical to the reference's
+        padding() + vgg_preprocess()/rtpose_preprocess() (estimator.py:52-68, preprocessing.py:16-43).
+        Returns (tensor, im_scale)."""
+        if not (_is_tensor(frames) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3):
+            raise ValueError("frames must be a CUDA uint8 tensor [n, H, W, 3] (BGR)")
+        frames = frames.contiguous()
+        n, sh, sw, _ = frames.shape
+        v = [C.c_int() for _ in range(4)]
+        scale = C.c_double()
+        _lib.check(_lib.lib.ekp_preprocess_dims(sh, sw, dest_size, factor, *[C.addressof(x) for x in v], C.addressof(scale)))
+        out = torch.empty((n, 3, v[2].value, v[3].value), dtype=torch.float32, device=frames.device)
+        _lib.check(_lib.lib.ekp_preprocess(self._ctx, frames.data_ptr(), n, sh, sw, dest_size, factor,
+                                           {"vgg": 0, "rtpose": 1}[mode], out.data_ptr(), self._stream(stream)))
+        return out, scale.value
+
     def kernel_launches(self) -> int:
         return int(_lib.lib.ekp_kernel_launches(self._ctx))
 
