@@ -123,6 +123,11 @@ int ekp_results(ekp_ctx *ctx, int *num_humans, float *subset, int *n_peaks, ekp_
  * float32 [n, max_humans] = subset[18] / subset[19] (get_score, pafprocess.cpp:204-206). */
 int ekp_results_humans(ekp_ctx *ctx, int *num_humans, ekp_peak *parts, float *scores, unsigned *overflow);
 
+/* Test hook: sorts scores (descending, comparator `a.score > b.score`, pafprocess.cpp:244-246) and
+ * the tags riding along with the device code's replay of libstdc++'s std::sort, in place, DEVICE
+ * pointers.  The resulting permutation of equal scores must equal the reference's (tests). */
+int ekp_debug_std_sort(ekp_ctx *ctx, float *scores, unsigned *tags, int n, void *stream);
+
 /* Per-part offsets into the peak table of the last run: int [n, 19]; part k of image i occupies
  * rows part_off[i][k] .. part_off[i][k+1]-1 of peaks_line (part_off[i][18] == n_peaks[i]). */
 int ekp_results_parts(ekp_ctx *ctx, int *part_off);

@@ -439,3 +439,36 @@ def test_input_side_kernel_vs_oracle(pp, shape, mode):
     got = out.cpu().numpy()
     for i in range(3):
         assert_bits_equal(got[i], fe.preprocess(frames[i], mode), f"frame {i}")
+
+
+def test_device_std_sort_replay_equals_libstdcxx(ek, pp):
+    """The device replay of libstdc++'s std::sort (used when >16 candidates tie) against the oracle's
+    restatement, itself pinned to the compiled reference's std::sort -- incl. median-of-3 killer
+    inputs that reach the heapsort fallback, which real scenes never do."""
+    port = util.port()
+    rng = np.random.default_rng(0)
+
+    def killer(n):
+        k = n // 2
+        a = np.zeros(n)
+        for i in range(k):
+            a[i] = i + 1 if i % 2 == 0 else k + i + 1
+            a[k + i] = 2 * (i + 1)
+        return (-a).astype(np.float32)
+
+    before = port.heapsort_hits()
+    for n in [0, 1, 2, 15, 16, 17, 18, 33, 64, 100, 257, 1000, 2048]:
+        for v in (rng.random(n), rng.integers(0, 3, n), np.zeros(n), np.sort(rng.integers(0, 9, n)), killer(n) if n > 1 else np.zeros(n)):
+            v = np.asarray(v, np.float32)
+            s = torch.from_numpy(v.copy()).cuda()
+            t = torch.arange(n, dtype=torch.int32).cuda()
+            ek._lib.check(ek._lib.lib.ekp_debug_std_sort(pp._ctx, s.data_ptr(), t.data_ptr(), n, 0))
+            torch.cuda.synchronize()
+            want_s, want_t = port.sort_scores(v)
+            assert np.array_equal(t.cpu().numpy(), want_t) and np.array_equal(s.cpu().numpy(), want_s), n
+    assert port.heapsort_hits() > before
+    ref = util.ref_or_none()
+    if ref is not None:   # and the oracle's restatement against the real std::sort on the same inputs
+        for n in (17, 100, 2048):
+            v = killer(n)
+            assert np.array_equal(port.sort_scores(v)[1], ref.sort_scores(v)[1])

@@ -45,6 +45,7 @@ SIGNATURES = {
     "ekp_process_paf_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "ekp_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "ekp_results_humans": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ekp_debug_std_sort": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ekp_results_parts": (_i, [_vp, _vp]),
     "ekp_dense_smooth_debug": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ekp_preprocess_dims": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

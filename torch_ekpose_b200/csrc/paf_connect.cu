@@ -318,6 +318,21 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     }
 }
 
+// Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one thread of one
+// block), so that the tie permutation -- including the heapsort fallback, which real scenes never
+// reach -- can be compared with the compiled reference's std::sort.
+__global__ void debug_std_sort_kernel(float* scores, unsigned* tags, int n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        CandArray A;
+        A.s = scores; A.t = tags;
+        std_sort_desc(A, n);
+    }
+}
+cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, cudaStream_t stream) {
+    debug_std_sort_kernel<<<1, 32, 0, stream>>>(scores, tags, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int max_peaks, const PafSource& paf, int h1,
                                int n, Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream) {
     dim3 grid(EKP_NUM_LIMB, n);
