@@ -95,24 +95,6 @@ struct CandArray {
     __device__ __forceinline__ bool comp(int i, int j) const { return s[i] > s[j]; }
 };
 
-__device__ void sort_unguarded_linear_insert(const CandArray& A, int last) {
-    const Cand val = A.get(last);
-    int next = last - 1;
-    while (val.s > A.s[next]) { A.set(last, A.get(next)); last = next; --next; }
-    A.set(last, val);
-}
-__device__ void sort_insertion(const CandArray& A, int first, int last) {
-    if (first == last) return;
-    for (int i = first + 1; i != last; ++i) {
-        if (A.comp(i, first)) {
-            const Cand val = A.get(i);
-            for (int k = i; k > first; --k) A.set(k, A.get(k - 1));
-            A.set(first, val);
-        } else {
-            sort_unguarded_linear_insert(A, i);
-        }
-    }
-}
 __device__ void sort_push_heap(const CandArray& A, int first, int hole, int top, Cand value) {
     int parent = (hole - 1) / 2;
     while (hole > top && A.s[first + parent] > value.s) {
@@ -155,8 +137,64 @@ __device__ void sort_heapsort(const CandArray& A, int first, int last) {  // __p
         sort_adjust_heap(A, first, 0, last - first, value);
     }
 }
+// ---- the same algorithm executed by ONE WARP ---------------------------------------------------
+// Control flow, comparisons and element moves are exactly libstdc++'s (same order), but every scan
+// ("advance while comp holds") inspects 32 elements per step with a ballot and every shift of the
+// insertion sort moves its elements in parallel.  All 32 lanes call these with identical arguments.
+__device__ __forceinline__ int lead_true(unsigned m) { return m == 0xffffffffu ? 32 : __ffs(~m) - 1; }
+
+// __unguarded_linear_insert(i) / the guarded branch of __insertion_sort: move element i left past
+// every element it is greater than (`lower` = lowest index that may be inspected).
+__device__ void warp_linear_insert(const CandArray& A, int i, int lower) {
+    const int lane = threadIdx.x & 31;
+    const Cand val = A.get(i);
+    int d = 0;  // number of elements val has to pass
+    for (;;) {
+        const int idx = i - 1 - d - lane;
+        const int run = lead_true(__ballot_sync(0xffffffffu, idx >= lower && val.s > A.s[idx]));
+        d += run;
+        if (run < 32) break;
+    }
+    if (d == 0) return;
+    for (int c0 = 0; c0 < d; c0 += 32) {  // shift [i-d, i-1] up by one, topmost chunk first
+        const int k = c0 + lane;
+        Cand t;
+        if (k < d) t = A.get(i - 1 - k);
+        __syncwarp();
+        if (k < d) A.set(i - k, t);
+        __syncwarp();
+    }
+    if (lane == 0) A.set(i - d, val);
+    __syncwarp();
+}
+
+// __unguarded_partition(lo, hi, pivot)
+__device__ int warp_partition(const CandArray& A, int lo, int hi, float pivot, int n) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        for (;;) {  // while (comp(lo, pivot)) ++lo;
+            const int idx = lo + lane;
+            const int run = lead_true(__ballot_sync(0xffffffffu, idx < n && A.s[idx] > pivot));
+            lo += run;
+            if (run < 32) break;
+        }
+        --hi;
+        for (;;) {  // while (comp(pivot, hi)) --hi;
+            const int idx = hi - lane;
+            const int run = lead_true(__ballot_sync(0xffffffffu, idx >= 0 && pivot > A.s[idx]));
+            hi -= run;
+            if (run < 32) break;
+        }
+        if (!(lo < hi)) return lo;
+        if (lane == 0) A.swap(lo, hi);
+        __syncwarp();
+        ++lo;
+    }
+}
+
 __device__ void std_sort_desc(const CandArray& A, int n) {
     if (n <= 0) return;
+    const int lane = threadIdx.x & 31;
     // __introsort_loop with an explicit stack: the recursion only ever touches disjoint ranges,
     // so the order in which they are finished does not change the result.
     int stk_first[48], stk_last[48], stk_depth[48];
@@ -168,10 +206,14 @@ __device__ void std_sort_desc(const CandArray& A, int n) {
         --sp;
         int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
         while (last - first > 16) {
-            if (depth == 0) { sort_heapsort(A, first, last); break; }
+            if (depth == 0) {  // heapsort fallback: never reached by real scenes, kept serial
+                if (lane == 0) sort_heapsort(A, first, last);
+                __syncwarp();
+                break;
+            }
             --depth;
             const int mid = first + (last - first) / 2;
-            {   // __move_median_to_first(first, first+1, mid, last-1)
+            if (lane == 0) {  // __move_median_to_first(first, first+1, mid, last-1)
                 const int a = first + 1, b = mid, c = last - 1;
                 if (A.comp(a, b)) {
                     if (A.comp(b, c)) A.swap(first, b);
@@ -181,27 +223,15 @@ __device__ void std_sort_desc(const CandArray& A, int n) {
                 else if (A.comp(b, c)) A.swap(first, c);
                 else A.swap(first, b);
             }
-            int lo = first + 1, hi = last;  // __unguarded_partition(first+1, last, pivot=first)
-            const float pivot = A.s[first];
-            for (;;) {
-                while (A.s[lo] > pivot) ++lo;
-                --hi;
-                while (pivot > A.s[hi]) --hi;
-                if (!(lo < hi)) break;
-                A.swap(lo, hi);
-                ++lo;
-            }
-            stk_first[sp] = lo; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
-            last = lo;
+            __syncwarp();
+            const int cut = warp_partition(A, first + 1, last, A.s[first], n);
+            stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
+            last = cut;
         }
     }
-    // __final_insertion_sort
-    if (n > 16) {
-        sort_insertion(A, 0, 16);
-        for (int i = 16; i < n; ++i) sort_unguarded_linear_insert(A, i);
-    } else {
-        sort_insertion(A, 0, n);
-    }
+    // __final_insertion_sort: __insertion_sort on the first 16 (or all), then unguarded inserts; both
+    // are "move left past everything smaller", bounded below by index 0
+    for (int i = 1; i < n; ++i) warp_linear_insert(A, i, 0);
 }
 
 __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_peak* __restrict__ line,
@@ -288,15 +318,15 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     }
     __syncthreads();
 
+    const bool replay = n > 16 && sTies;  // uniform
+    if (replay && threadIdx.x < 32) {    // warp 0 replays libstdc++'s std::sort on the original sequence
+        CandArray A;
+        A.s = sScore; A.t = sTag;
+        std_sort_desc(A, n);
+    }
     if (threadIdx.x == 0) {
-        const float* srcS = sScore2;
-        const unsigned* srcT = sTag2;
-        if (n > 16 && sTies) {
-            CandArray A;
-            A.s = sScore; A.t = sTag;
-            std_sort_desc(A, n);
-            srcS = sScore; srcT = sTag;
-        }
+        const float* srcS = replay ? sScore : sScore2;
+        const unsigned* srcT = replay ? sTag : sTag2;
         // greedy assignment, pafprocess.cpp:98-124 (a peak is used at most once per limb side)
         unsigned usedA[EKP_MAX_PART / 32], usedB[EKP_MAX_PART / 32];
 #pragma unroll
@@ -318,15 +348,12 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     }
 }
 
-// Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one thread of one
-// block), so that the tie permutation -- including the heapsort fallback, which real scenes never
+// Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one warp), so that the tie permutation -- including the heapsort fallback, which real scenes never
 // reach -- can be compared with the compiled reference's std::sort.
 __global__ void debug_std_sort_kernel(float* scores, unsigned* tags, int n) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        CandArray A;
-        A.s = scores; A.t = tags;
-        std_sort_desc(A, n);
-    }
+    CandArray A;  // one warp, as in paf_connect_kernel
+    A.s = scores; A.t = tags;
+    std_sort_desc(A, n);
 }
 cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, cudaStream_t stream) {
     debug_std_sort_kernel<<<1, 32, 0, stream>>>(scores, tags, n);
