@@ -472,3 +472,60 @@ def test_device_std_sort_replay_equals_libstdcxx(ek, pp):
         for n in (17, 100, 2048):
             v = killer(n)
             assert np.array_equal(port.sort_scores(v)[1], ref.sort_scores(v)[1])
+
+
+def test_host_entry_equals_device_entry(ek):
+    """ekp_postprocess_host (pinned / pageable host buffers, the e2e path of bench.py) must give exactly
+    what ekp_postprocess gives on device tensors, with and without materialisation."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(8, 46, 54, (1, 6), seed=31)
+    a = ek.PostProcessor(device=0, max_batch=8, max_h=46, max_w=54, max_peaks=512, max_humans=32)
+    b = ek.PostProcessor(device=0, max_batch=8, max_h=46, max_w=54, max_peaks=512, max_humans=32)
+    for frontend in ("dense", "reference"):
+        for mat in (True, False):
+            a.run(_dev(heat), _dev(paf), frontend=frontend, materialize=mat)
+            b.run(torch.from_numpy(heat).pin_memory(), torch.from_numpy(paf).pin_memory(), frontend=frontend, materialize=mat)
+            ra, rb = a.results(with_peaks=True), b.results(with_peaks=True)
+            for k in ("num_humans", "n_peaks", "overflow", "part_off"):
+                assert np.array_equal(ra[k], rb[k]), (frontend, mat, k)
+            assert np.array_equal(ra["subset"].view(np.uint32), rb["subset"].view(np.uint32))
+            assert np.array_equal(ra["peaks"], rb["peaks"])
+            ha, hb = a.human_tables(), b.human_tables()
+            assert all(np.array_equal(x, y) for x, y in zip(ha, hb))
+    a.close(); b.close()
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from torch_ekpose_b200 import synthetic
+    from torch_ekpose_b200.sharding import postprocess_sharded
+    heat, paf = synthetic.make_batch(9, 46, 54, (1, 4), seed=41)
+    num, sub = postprocess_sharded(heat, paf, frontend="dense", max_humans=32, max_peaks=512)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), num=num, sub=sub)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_sharded_two_gpus_nccl(ek, tmp_path):
+    """One process per GPU, images sharded, final gather over NCCL == single-GPU result."""
+    import socket
+    import torch.multiprocessing as mp
+    from torch_ekpose_b200 import synthetic
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    heat, paf = synthetic.make_batch(9, 46, 54, (1, 4), seed=41)
+    one = ek.PostProcessor(device=0, max_batch=9, max_h=46, max_w=54, max_peaks=512, max_humans=32)
+    one.run(_dev(heat), _dev(paf), frontend="dense")
+    want = one.results()
+    one.close()
+    for r in range(2):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        assert np.array_equal(z["num"], want["num_humans"])
+        assert np.array_equal(z["sub"].view(np.uint32), want["subset"].view(np.uint32))

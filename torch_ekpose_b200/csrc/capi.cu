@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -416,7 +417,9 @@ extern "C" int ekp_results(ekp_ctx* c, int* num_humans, float* subset, int* n_pe
     if (peaks_line) {  // the big table is only fetched on request
         CU(cudaMemcpyAsync(c->h_line, c->line, sizeof(ekp_peak) * (size_t) n * c->max_peaks, cudaMemcpyDeviceToHost, c->last_stream));
         CU(cudaStreamSynchronize(c->last_stream));
-        memcpy(peaks_line, c->h_line, sizeof(ekp_peak) * (size_t) n * c->max_peaks);
+        for (int i = 0; i < n; i++)  // only the valid rows: what lies behind them in the work buffer is stale
+            memcpy(peaks_line + (size_t) i * c->max_peaks, c->h_line + (size_t) i * c->max_peaks,
+                   sizeof(ekp_peak) * (size_t) std::min(rec_head(c, i)->n_peaks, c->max_peaks));
     }
     return overflow_status(c);
 }
