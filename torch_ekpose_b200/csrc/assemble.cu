@@ -30,16 +30,37 @@ __host__ __device__ constexpr int limb_b(int l) {
     return t[l];
 }
 
+// Everything the sequential loop needs about one connection, prepared in parallel while staging:
+// the cids as floats (rows hold floats) and the two score sums the reference forms
+// (pafprocess.cpp:150/171: peak(cid2) + conn;  :179-181: (peak(cid1) + peak(cid2)) + conn), same order.
+struct __align__(16) ConnRec {
+    float f1, f2;   // (float) cid1, (float) cid2
+    float score;    // connection score
+    float s_ext;    // peak_score(cid2) + score        (a row is extended by part2)
+    float s_new;    // (peak_score(cid1) + peak_score(cid2)) + score   (a new row)
+    float pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ ConnRec make_rec(const Conn& cn, const ekp_peak* L) {
+    ConnRec r;
+    r.f1 = (float) cn.cid1;
+    r.f2 = (float) cn.cid2;
+    r.score = cn.score;
+    const float p1 = L[cn.cid1].score, p2 = L[cn.cid2].score;
+    r.s_ext = __fadd_rn(p2, cn.score);
+    r.s_new = __fadd_rn(__fadd_rn(p1, p2), cn.score);
+    r.pad0 = r.pad1 = r.pad2 = 0.f;
+    return r;
+}
+
 struct AsmInput {
-    const Conn* sConn;    // staged connections (or nullptr -> read `conns`)
+    const ConnRec* sRec;  // staged records (or nullptr -> build from `conns` / `L` on the fly)
     const int* sStart;    // [20] prefix of per-limb counts
-    const float* sScore;  // staged peak scores (or nullptr -> read `L`)
     const Conn* conns;    // this image's [19][EKP_MAX_PART]
     const ekp_peak* L;    // this image's part-sorted peak table
-    __device__ __forceinline__ Conn conn_at(int limb, int k) const {
-        return sConn ? sConn[sStart[limb] + k] : conns[(size_t) limb * EKP_MAX_PART + k];
+    __device__ __forceinline__ ConnRec rec_at(int limb, int k) const {
+        return sRec ? sRec[sStart[limb] + k] : make_rec(conns[(size_t) limb * EKP_MAX_PART + k], L);
     }
-    __device__ __forceinline__ float score_of(int cid) const { return sScore ? sScore[cid] : L[cid].score; }
 };
 
 // ---- fast path: R subset rows per lane, in registers ------------------------------------------
@@ -62,8 +83,8 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
         const int p1 = limb_a(limb), p2 = limb_b(limb);
         const int nc = in.sStart[limb + 1] - in.sStart[limb];
         for (int k = 0; k < nc; k++) {
-            const Conn cn = in.conn_at(limb, k);
-            const float f1 = (float) cn.cid1, f2 = (float) cn.cid2;
+            const ConnRec cn = in.rec_at(limb, k);
+            const float f1 = cn.f1, f2 = cn.f2;
             // row search (pafprocess.cpp:137-144): first two matches in row order, and the count
             int found = 0, s1 = 0, s2 = 0;
             bool m[R];
@@ -89,7 +110,7 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
                     if (m[s] && r[s][p2] != f2) {
                         r[s][p2] = f2;
                         r[s][19] = __fadd_rn(r[s][19], 1.0f);
-                        r[s][18] = __fadd_rn(r[s][18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                        r[s][18] = __fadd_rn(r[s][18], cn.s_ext);
                     }
             } else if (found == 2) {
                 const int l1 = s1 & 31, l2 = s2 & 31, t1 = s1 >> 5, t2 = s2 >> 5;
@@ -138,7 +159,7 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
                         if (lane == l1 && t1 == s) {
                             r[s][p2] = f2;
                             r[s][19] = __fadd_rn(r[s][19], 1.0f);
-                            r[s][18] = __fadd_rn(r[s][18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                            r[s][18] = __fadd_rn(r[s][18], cn.s_ext);
                         }
                 }
             } else if (found == 0 && limb < 18) {
@@ -151,7 +172,7 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
                         r[s][p1] = f1;
                         r[s][p2] = f2;
                         r[s][19] = 2.0f;
-                        r[s][18] = __fadd_rn(__fadd_rn(in.score_of(cn.cid1), in.score_of(cn.cid2)), cn.score);
+                        r[s][18] = cn.s_new;
                     }
                 nrows++;
             }
@@ -178,8 +199,8 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
         const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
         const int nc = in.sStart[limb + 1] - in.sStart[limb];
         for (int k = 0; k < nc; k++) {
-            const Conn cn = in.conn_at(limb, k);
-            const float f1 = (float) cn.cid1, f2 = (float) cn.cid2;
+            const ConnRec cn = in.rec_at(limb, k);
+            const float f1 = cn.f1, f2 = cn.f2;
             int found = 0, s1 = 0, s2 = 0;
             for (int base = 0; base < nrows; base += 32) {
                 const int r = base + lane;
@@ -201,7 +222,7 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
                 if (lane == 0 && rows[s1 * 20 + p2] != f2) {
                     rows[s1 * 20 + p2] = f2;
                     rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
                 }
             } else if (found == 2) {
                 const bool both = lane < 18 && rows[s1 * 20 + lane] > 0.f && rows[s2 * 20 + lane] > 0.f;
@@ -220,7 +241,7 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
                 } else if (lane == 0) {
                     rows[s1 * 20 + p2] = f2;
                     rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], __fadd_rn(in.score_of(cn.cid2), cn.score));
+                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
                 }
             } else if (found == 0 && limb < 18) {
                 if (nrows < max_humans) {
@@ -229,7 +250,7 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
                         if (lane == p1) v = f1;
                         if (lane == p2) v = f2;
                         if (lane == 19) v = 2.0f;
-                        if (lane == 18) v = __fadd_rn(__fadd_rn(in.score_of(cn.cid1), in.score_of(cn.cid2)), cn.score);
+                        if (lane == 18) v = cn.s_new;
                         rows[nrows * 20 + lane] = v;
                     }
                     nrows++;
@@ -246,13 +267,12 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
 __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict__ line, int max_peaks,
                                                       const int* __restrict__ n_peaks, const Conn* __restrict__ conns,
                                                       const int* __restrict__ n_conns, int max_humans, int conn_cap,
-                                                      int score_cap, const unsigned* __restrict__ overflow,
+                                                      const unsigned* __restrict__ overflow,
                                                       unsigned char* __restrict__ records, ResultLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* rows = reinterpret_cast<float*>(smem_raw);                                        // [max(max_humans, 32)][20]
-    Conn* sConn = reinterpret_cast<Conn*>(rows + (size_t) (max_humans < 32 ? 32 : max_humans) * 20);  // [conn_cap]
-    float* sScore = reinterpret_cast<float*>(sConn + conn_cap);                              // [score_cap]
-    int* sKept = reinterpret_cast<int*>(sScore + score_cap);                                 // [max_humans]
+    float* rows = reinterpret_cast<float*>(smem_raw);                                             // [max(max_humans, 32)][20]
+    ConnRec* sRec = reinterpret_cast<ConnRec*>(rows + (size_t) (max_humans < 32 ? 32 : max_humans) * 20);  // [conn_cap]
+    int* sKept = reinterpret_cast<int*>(sRec + conn_cap);                                         // [max_humans]
     __shared__ int sStart[EKP_NUM_LIMB + 1];
 
     const int img = blockIdx.x, lane = threadIdx.x;
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     const Conn* Cimg = conns + (size_t) img * EKP_NUM_LIMB * EKP_MAX_PART;
     const int npk = n_peaks[img];
 
-    // ---- stage connections and peak scores --------------------------------------------------
+    // ---- stage one prepared record per connection ------------------------------------------------
     int cnt = 0;
     if (lane < EKP_NUM_LIMB) cnt = min(n_conns[(size_t) img * EKP_NUM_LIMB + lane], EKP_MAX_PART);
     int incl = cnt;  // inclusive prefix over the 19 limbs
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     if (lane == EKP_NUM_LIMB - 1) sStart[EKP_NUM_LIMB] = incl;
     __syncwarp();
     const int total_conns = sStart[EKP_NUM_LIMB];
-    const bool staged = total_conns <= conn_cap && npk <= score_cap;
+    const bool staged = total_conns <= conn_cap;
     if (staged) {
         // one flat pass so that all loads are in flight together (a per-limb loop would pay one
         // global-memory round trip per limb)
@@ -281,15 +301,13 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
             int limb = 0;
 #pragma unroll
             for (int l = 1; l < EKP_NUM_LIMB; l++) limb += (idx >= sStart[l]);
-            sConn[idx] = Cimg[(size_t) limb * EKP_MAX_PART + (idx - sStart[limb])];
+            sRec[idx] = make_rec(Cimg[(size_t) limb * EKP_MAX_PART + (idx - sStart[limb])], L);
         }
-        for (int k = lane; k < npk; k += 32) sScore[k] = L[k].score;
     }
     __syncwarp();
     AsmInput in;
-    in.sConn = staged ? sConn : nullptr;
+    in.sRec = staged ? sRec : nullptr;
     in.sStart = sStart;
-    in.sScore = staged ? sScore : nullptr;
     in.conns = Cimg;
     in.L = L;
 
@@ -353,28 +371,23 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     }
 }
 
-static size_t assemble_smem(int max_humans, int conn_cap, int score_cap) {
+static size_t assemble_smem(int max_humans, int conn_cap) {
     const size_t nrow = (size_t) (max_humans < 32 ? 32 : max_humans);
-    return sizeof(float) * 20 * nrow + sizeof(Conn) * (size_t) conn_cap + sizeof(float) * (size_t) score_cap + sizeof(int) * nrow;
+    return sizeof(float) * 20 * nrow + sizeof(ConnRec) * (size_t) conn_cap + sizeof(int) * nrow;
 }
-void assemble_caps(int max_peaks, int* conn_cap, int* score_cap) {
-    *conn_cap = 2 * max_peaks < 2048 ? 2 * max_peaks : 2048;
-    *score_cap = max_peaks < 4096 ? max_peaks : 4096;
-}
+static int assemble_conn_cap(int max_peaks) { return 2 * max_peaks < 1536 ? 2 * max_peaks : 1536; }
 
 cudaError_t configure_assemble(int max_humans, int max_peaks) {
-    int cc, sc;
-    assemble_caps(max_peaks, &cc, &sc);
-    return cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) assemble_smem(max_humans, cc, sc));
+    return cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) assemble_smem(max_humans, assemble_conn_cap(max_peaks)));
 }
 
 cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,
                             int max_humans, int n, const unsigned* overflow, unsigned char* records, const ResultLayout& lay,
                             cudaStream_t stream) {
-    int cc, sc;
-    assemble_caps(max_peaks, &cc, &sc);
-    assemble_kernel<<<n, 32, assemble_smem(max_humans, cc, sc), stream>>>(line, max_peaks, n_peaks, conns, n_conns, max_humans, cc,
-                                                                        sc, overflow, records, lay);
+    const int cc = assemble_conn_cap(max_peaks);
+    assemble_kernel<<<n, 32, assemble_smem(max_humans, cc), stream>>>(line, max_peaks, n_peaks, conns, n_conns, max_humans, cc,
+                                                                    overflow, records, lay);
     return cudaGetLastError();
 }
 
