@@ -11,10 +11,10 @@
 //
 // A single warp running dependent code pays full latency on every instruction, so:
 //  * the image's connections and peak scores are staged in shared memory first (coalesced);
-//  * while the image has at most 32 candidate people, lane r keeps subset row r in REGISTERS
-//    (the 19-limb loop is unrolled so every column index is a compile-time constant); a
-//    connection then costs one broadcast load, two compares and a ballot.  A 33rd row restarts
-//    the image on the general shared-memory path below (same arithmetic, any row count);
+//  * up to 64 candidate people live in REGISTERS, two subset rows per lane (the 19-limb loop is
+//    unrolled so every column index is a compile-time constant); extending or starting a row costs
+//    one broadcast load, two compares and two ballots.  Merges and a 65th row continue, from the
+//    same connection, on the general shared-memory path below (same arithmetic, any row count);
 //  * results go to one packed record per image (ResultLayout): one device-to-host copy per batch.
 #include "common.cuh"
 
@@ -64,10 +64,16 @@ struct AsmInput {
 };
 
 // ---- fast path: R subset rows per lane, in registers ------------------------------------------
-// Row index i lives in lane (i & 31), slot (i >> 5); capacity 32*R rows.  Returns false (outputs
-// undefined) when one more row would be needed; the caller then uses a larger R or the general path.
+// Row index i lives in lane (i & 31), slot (i >> 5); capacity 32*R rows.  It handles the two cases
+// that make up almost every step -- a connection extends one row (found == 1) or starts a new one
+// (found == 0) -- with one broadcast load, R compares and R ballots.  When a connection matches
+// TWO rows (a merge, rare) or a row beyond the capacity is needed, the rows are written to shared
+// memory and the caller continues from exactly that connection on the general path.  The 19-limb
+// loop is unrolled (column indices must be compile-time for registers), so the per-limb body is
+// kept this small on purpose: the whole path has to stay inside the instruction cache.
 template <int R>
-__device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float* __restrict__ rows_out, int& nrows_out) {
+__device__ void assemble_in_registers(const AsmInput& in, int max_humans, float* __restrict__ rows_out, int& nrows_out,
+                                      int& resume_limb, int& resume_k) {
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
     float r[R][20];
@@ -77,109 +83,52 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
         for (int q = 0; q < 20; q++) r[s][q] = -1.0f;
     int nrows = 0;
     const int cap = max_humans < 32 * R ? max_humans : 32 * R;
-    bool fits = true;
+    resume_limb = EKP_NUM_LIMB;  // "finished"
+    resume_k = 0;
+    bool bail = false;
 #pragma unroll
     for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
         const int p1 = limb_a(limb), p2 = limb_b(limb);
         const int nc = in.sStart[limb + 1] - in.sStart[limb];
         for (int k = 0; k < nc; k++) {
             const ConnRec cn = in.rec_at(limb, k);
-            const float f1 = cn.f1, f2 = cn.f2;
-            // row search (pafprocess.cpp:137-144): first two matches in row order, and the count
-            int found = 0, s1 = 0, s2 = 0;
+            int found = 0;
             bool m[R];
 #pragma unroll
-            for (int s = 0; s < R; s++) {
-                m[s] = (32 * s + lane) < nrows && (r[s][p1] == f1 || r[s][p2] == f2);
-                unsigned mask = __ballot_sync(FULL, m[s]);
-                const int c = __popc(mask);
-                if (c) {
-                    if (found == 0) {
-                        s1 = 32 * s + __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        if (mask) s2 = 32 * s + __ffs(mask) - 1;
-                    } else if (found == 1) {
-                        s2 = 32 * s + __ffs(mask) - 1;
-                    }
-                    found += c;
-                }
+            for (int s = 0; s < R; s++) {  // row search, pafprocess.cpp:137-144
+                m[s] = (32 * s + lane) < nrows && (r[s][p1] == cn.f1 || r[s][p2] == cn.f2);
+                found += __popc(__ballot_sync(FULL, m[s]));
             }
             if (found == 1) {
 #pragma unroll
                 for (int s = 0; s < R; s++)
-                    if (m[s] && r[s][p2] != f2) {
-                        r[s][p2] = f2;
+                    if (m[s] && r[s][p2] != cn.f2) {
+                        r[s][p2] = cn.f2;
                         r[s][19] = __fadd_rn(r[s][19], 1.0f);
                         r[s][18] = __fadd_rn(r[s][18], cn.s_ext);
                     }
-            } else if (found == 2) {
-                const int l1 = s1 & 31, l2 = s2 & 31, t1 = s1 >> 5, t2 = s2 >> 5;
-                float o[20], mine[20];  // row s2 broadcast to every lane; lane l1's own copy of row s1
-#pragma unroll
-                for (int q = 0; q < 20; q++) {
-                    float v2 = r[0][q], v1 = r[0][q];
-#pragma unroll
-                    for (int s = 1; s < R; s++) {
-                        if (t2 == s) v2 = r[s][q];
-                        if (t1 == s) v1 = r[s][q];
-                    }
-                    o[q] = __shfl_sync(FULL, v2, l2);
-                    mine[q] = v1;
-                }
-                bool both = false;
-#pragma unroll
-                for (int q = 0; q < 18; q++) both |= (mine[q] > 0.f && o[q] > 0.f);
-                const bool membership = __shfl_sync(FULL, (int) both, l1) != 0;
-                if (!membership) {
+            } else if (found == 0) {
+                if (limb < 18) {
+                    if (nrows >= cap) { bail = true; resume_limb = limb; resume_k = k; break; }
 #pragma unroll
                     for (int s = 0; s < R; s++)
-                        if (lane == l1 && t1 == s) {
+                        if (32 * s + lane == nrows) {
 #pragma unroll
-                            for (int q = 0; q < 18; q++) r[s][q] = __fadd_rn(r[s][q], __fadd_rn(o[q], 1.0f));
-                            r[s][19] = __fadd_rn(r[s][19], o[19]);
-                            r[s][18] = __fadd_rn(__fadd_rn(r[s][18], o[18]), cn.score);
+                            for (int q = 0; q < 18; q++) r[s][q] = -1.0f;
+                            r[s][p1] = cn.f1;
+                            r[s][p2] = cn.f2;
+                            r[s][19] = 2.0f;
+                            r[s][18] = cn.s_new;
                         }
-                    // erase row s2: every row above it moves down by one index
-#pragma unroll
-                    for (int q = 0; q < 20; q++) {
-                        float head[R];  // lane 0's value of each slot (what lane 31 of the slot below inherits)
-#pragma unroll
-                        for (int s = 0; s < R; s++) head[s] = __shfl_sync(FULL, r[s][q], 0);
-#pragma unroll
-                        for (int s = 0; s < R; s++) {
-                            float nx = __shfl_down_sync(FULL, r[s][q], 1);
-                            if (lane == 31) nx = (s + 1 < R) ? head[s + 1 < R ? s + 1 : s] : r[s][q];
-                            if (32 * s + lane >= s2) r[s][q] = nx;
-                        }
-                    }
-                    nrows--;
-                } else {
-#pragma unroll
-                    for (int s = 0; s < R; s++)
-                        if (lane == l1 && t1 == s) {
-                            r[s][p2] = f2;
-                            r[s][19] = __fadd_rn(r[s][19], 1.0f);
-                            r[s][18] = __fadd_rn(r[s][18], cn.s_ext);
-                        }
+                    nrows++;
                 }
-            } else if (found == 0 && limb < 18) {
-                if (nrows >= cap) { fits = false; break; }
-#pragma unroll
-                for (int s = 0; s < R; s++)
-                    if (32 * s + lane == nrows) {
-#pragma unroll
-                        for (int q = 0; q < 18; q++) r[s][q] = -1.0f;
-                        r[s][p1] = f1;
-                        r[s][p2] = f2;
-                        r[s][19] = 2.0f;
-                        r[s][18] = cn.s_new;
-                    }
-                nrows++;
-            }
+            } else if (found == 2) {  // merge or extend-with-conflict: continue on the general path
+                bail = true; resume_limb = limb; resume_k = k;
+                break;
+            }  // found >= 3: the reference takes no branch
         }
-        if (!fits) break;
+        if (bail) break;
     }
-    if (!fits) return false;
 #pragma unroll
     for (int s = 0; s < R; s++)
         if (32 * s + lane < nrows) {
@@ -188,17 +137,18 @@ __device__ bool assemble_in_registers(const AsmInput& in, int max_humans, float*
         }
     nrows_out = nrows;
     __syncwarp();
-    return true;
 }
 
 // ---- general path: rows in shared memory, any count up to max_humans ---------------------------
-__device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __restrict__ rows, int& nrows_out, bool& ovf) {
+// Starts at connection k0 of limb limb0 with nrows_io rows already in `rows`.
+__device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __restrict__ rows, int& nrows_io, bool& ovf,
+                                 int limb0, int k0) {
     const int lane = threadIdx.x;
-    int nrows = 0;
-    for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
+    int nrows = nrows_io;
+    for (int limb = limb0; limb < EKP_NUM_LIMB; limb++) {
         const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
         const int nc = in.sStart[limb + 1] - in.sStart[limb];
-        for (int k = 0; k < nc; k++) {
+        for (int k = (limb == limb0 ? k0 : 0); k < nc; k++) {
             const ConnRec cn = in.rec_at(limb, k);
             const float f1 = cn.f1, f2 = cn.f2;
             int found = 0, s1 = 0, s2 = 0;
@@ -261,7 +211,7 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
             __syncwarp();
         }
     }
-    nrows_out = nrows;
+    nrows_io = nrows;
 }
 
 __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict__ line, int max_peaks,
@@ -314,16 +264,11 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     // ---- sequential assembly ------------------------------------------------------------------
     int nrows = 0;
     bool ovf = false;
-    // People per image ~ the largest per-limb connection count; pick the register capacity from it
-    // (32, 64 or 128 rows) and fall back to the next larger one, finally to shared memory.
-    int max_conn = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) max_conn = max(max_conn, __shfl_xor_sync(0xffffffffu, max_conn, o));
-    bool done = false;
-    if (max_conn <= 24) done = assemble_in_registers<1>(in, max_humans, rows, nrows);
-    if (!done && max_conn <= 56 && max_humans > 32) done = assemble_in_registers<2>(in, max_humans, rows, nrows);
-    if (!done && max_conn <= 120 && max_humans > 64) done = assemble_in_registers<4>(in, max_humans, rows, nrows);
-    if (!done) assemble_in_smem(in, max_humans, rows, nrows, ovf);
+    // Registers hold up to 64 rows (two per lane); whatever they cannot do (merges, more rows) continues
+    // on the shared-memory path from the connection where they stopped.
+    int resume_limb = 0, resume_k = 0;
+    if (max_humans >= 1) assemble_in_registers<2>(in, max_humans, rows, nrows, resume_limb, resume_k);
+    if (resume_limb < EKP_NUM_LIMB) assemble_in_smem(in, max_humans, rows, nrows, ovf, resume_limb, resume_k);
     __syncwarp();
 
     // ---- prune (pafprocess.cpp:187-191: a reverse erase loop == an order-preserving filter) and
