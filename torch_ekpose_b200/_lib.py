@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libekpose_b200.so")
+# EKPOSE_B200_SO selects another build of the same library (kernel sweeps in tools/)
+SO_PATH = os.environ.get("EKPOSE_B200_SO") or os.path.join(HERE, "libekpose_b200.so")
 
 NUM_PART, NUM_LIMB, HEAT_CH, PAF_CH, UP, SUBSET_COLS = 18, 19, 19, 38, 8, 20
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1

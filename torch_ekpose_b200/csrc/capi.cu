@@ -17,7 +17,7 @@
 
 namespace ekp {
 // kernels (one translation unit each)
-size_t dense_frontend_smem_bytes(int tile_wl);
+size_t dense_frontend_smem_bytes(int tile_wl, bool materialise);
 int dense_frontend_tile_wl(int w);
 cudaError_t configure_dense_frontend();
 cudaError_t set_interior_taps(const float* taps64);

@@ -1,15 +1,15 @@
 // dense_frontend.cu -- stages 1-3 of the hot path, fused, for sm_100a.
 //
 // One launch takes the network's stride-8 heat (19 ch) and PAF (38 ch) maps of a whole batch
-// and, per 16-row x (8*tile_wl)-column full-resolution tile (one CTA of 256 threads, 3 CTAs/SM),
+// and, per 16-row x (8*tile_wl)-column full-resolution tile (one CTA),
 //   (0) first wave of CTAs only: prefetches the whole batch's inputs into L2 (evict_last) in one
 //       burst, so input reads do not trickle in between the writes (HBM read/write turnarounds),
-//   (1) stages the stride-8 neighbourhood of the tile in shared memory (HWC order) with cp.async
-//       in two groups, PAF first,
+//   (1) stages the stride-8 neighbourhood of the tile in shared memory (HWC order) with cp.async,
 //   (2) optionally materialises the bilinear x8 tensors heat_mat[H][W][19] / paf_mat[H][W][38]
-//       (the operator-surface tensors of process_paf, paf_to_pose.py:356-360) with 16-byte
-//       coalesced streaming stores -- the HBM-bound part: 36.25 MB written per 368x432 image
-//       against 0.57 MB read; paf_mat is streamed out while the heat patch is still in flight,
+//       (the operator-surface tensors of process_paf, paf_to_pose.py:356-360) -- the HBM-bound part:
+//       36.25 MB written per 368x432 image against 0.57 MB read.  The rows are built in
+//       shared-memory store buffers and written by the TMA engine (cp.async.bulk shared -> global,
+//       4 KB contiguous per copy), so no warp ever waits on a store,
 //   (3) evaluates the Gaussian-smoothed (sigma 3, 25 taps, reflect) bilinear-upsampled heat map
 //       as ONE separable 5-tap polyphase filter on the stride-8 grid (the composition of the two
 //       linear operators; tables built on the host in capi.cu) entirely in registers -- only for
@@ -17,47 +17,68 @@
 //       (exact early-out from a per-tile column-maximum table),
 //   (4) does the 3x3 max NMS with warp shuffles (x) and a rolling 3-row window (y) and appends
 //       peaks with a warp-ballot aggregated atomic into the per-image raw peak list.
-// heat_mat chunks and surviving NMS strips are handed out to the warps dynamically, so stores keep
-// flowing while the smoothing runs.  Nothing but the (optional) operator-surface tensors and the
-// peaks ever goes back to HBM.
+// When materialising, the CTA's warps are specialised: "fill" warps feed the TMA engine, the others do
+// (3)-(4) underneath the store stream (process_tile_mat).  Nothing but the (optional)
+// operator-surface tensors and the peaks ever goes back to HBM.
 //
 // Arithmetic is the one defined in oracle/frontend_oracle.c part (B); results are bit-identical
 // to it (tests/test_gpu_parity.py).  There is no reference implementation of this front-end
 // (SURVEY.md 0.1); the reference's own front-end is ref_frontend.cu.
 //
-// Why no TMA: cuTensorMap strides must be multiples of 16 bytes; the rows of these tensors are
-// 54 (or 82, 164) floats and the pixels 19 / 38 floats, so neither the NCHW nor the NHWC input
+// TMA: the OUTPUT side uses the TMA engine's plain bulk copies (16-byte aligned row segments).  The
+// INPUT side cannot: cuTensorMap strides must be multiples of 16 bytes, the rows of these tensors
+// are 54 (or 82, 164) floats and the pixels 19 / 38 floats, so neither the NCHW nor the NHWC input
 // can be described by a tiled tensor map without re-padding it, and the NCHW -> HWC transpose
 // that the staging performs on the fly is not a box copy.  4-byte cp.async (LDGSTS) does both.
 //
-// The kernel started issue-slot bound (666 M warp instructions, 0.50 of the HBM roofline) and is
-// now store-stream bound (145 M, 0.92): see profiles/README.md for the ncu history and ablations.
+// History (profiles/README.md): issue-slot bound at 0.50 of the measured HBM roofline (666 M warp
+// instructions) -> per-thread streaming stores at 0.92 (145 M) -> TMA bulk stores + warp roles 0.94.
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace ekp {
 
-#ifndef EKP_ROW_BATCH
-#define EKP_ROW_BATCH 4
+#ifndef EKP_LEAN_THREADS
+#define EKP_LEAN_THREADS 256
 #endif
-#ifndef EKP_MIN_BLOCKS
-#define EKP_MIN_BLOCKS 3
+#ifndef EKP_LEAN_BLOCKS
+#define EKP_LEAN_BLOCKS 3
 #endif
-#ifndef EKP_THREADS
-#define EKP_THREADS 256
+#ifndef EKP_MAT_THREADS
+#define EKP_MAT_THREADS 384
+#endif
+#ifndef EKP_MAT_BLOCKS
+#define EKP_MAT_BLOCKS 2
+#endif
+#ifndef EKP_FILL_WARPS
+#define EKP_FILL_WARPS 8
+#endif
+#ifndef EKP_STORE_BUFS
+#define EKP_STORE_BUFS 2
+#endif
+#ifndef EKP_CHUNK_COLS
+#define EKP_CHUNK_COLS 256
 #endif
 #ifndef EKP_MAX_TWL
 #define EKP_MAX_TWL 32
 #endif
-constexpr int kRowBatch = EKP_ROW_BATCH;  // output rows whose stores are kept in flight together
-constexpr int kThreads = EKP_THREADS;
-constexpr int kMaxTwl = EKP_MAX_TWL;      // widest tile in stride-8 columns
-constexpr unsigned kPrefetchCtas = 148u * EKP_MIN_BLOCKS;  // one resident wave on a B200
-#ifndef EKP_NMS_WARPS
-#define EKP_NMS_WARPS 2
-#endif
-constexpr int kNmsWarps = EKP_NMS_WARPS;  // warps that start on NMS strips rather than heat_mat chunks
+constexpr int kMaxTwl = EKP_MAX_TWL;          // widest tile in stride-8 columns
+constexpr int kLeanThreads = EKP_LEAN_THREADS;  // CTA size / resident CTAs per SM without materialisation
+constexpr int kLeanBlocks = EKP_LEAN_BLOCKS;
+constexpr int kMatThreads = EKP_MAT_THREADS;    // ... with it (the store buffers take shared memory: 2 CTAs per SM)
+constexpr int kMatBlocks = EKP_MAT_BLOCKS;
+constexpr int kFillWarps = EKP_FILL_WARPS;      // warps that fill the store buffers and drive the TMA engine
+constexpr int kFillThreads = 32 * kFillWarps;
+constexpr int kNmsThreads = kMatThreads - kFillThreads;  // the other warps: heat patch, early-out, smoothing + NMS
+constexpr int kStoreBufs = EKP_STORE_BUFS;      // store buffers of [8 rows][kChunkCols float4] per CTA
+constexpr int kChunkCols = EKP_CHUNK_COLS;      // float4 columns per store chunk: one bulk copy = kChunkCols * 16 B of a row
+constexpr int kColsPerFillThread = kChunkCols / kFillThreads;
+constexpr int kStoreBufF4 = 8 * kChunkCols;
+static_assert(kFillWarps >= 1 && kNmsThreads >= 32 && kNmsThreads % 32 == 0 && kChunkCols % kFillThreads == 0, "warp roles");
+enum { BAR_FILL = 1, BAR_NMS = 2, BAR_HEAT_READY = 3 };  // named barriers (0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 constexpr int kTH = 16;             // full-resolution rows per tile
 constexpr int kTB = kTH / 8;        // stride-8 row blocks per tile
 constexpr int kHeatRows = kTB + 6;  // stride-8 rows staged for the smoothing window
@@ -86,14 +107,15 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 
 template <int C>
 __device__ __forceinline__ void stage_patch(float* __restrict__ sP, const float* __restrict__ src, int layout,
-                                            int img, int h, int w, int r0, int r1, int c0, int c1, int pcols) {
+                                            int img, int h, int w, int r0, int r1, int c0, int c1, int pcols,
+                                            unsigned tid, unsigned nthr) {
     const int nr = r1 - r0 + 1, nc = c1 - c0 + 1;
     if (layout == EKP_LAYOUT_NCHW) {
         const unsigned plane = nr * nc, total = C * plane;
         const unsigned m_plane = magic_of(plane), m_nc = magic_of(nc);  // uniform, a handful of instructions
         const float* g0 = src + ((size_t) img * C * h + r0) * w + c0;
         const int hw = h * w;
-        for (unsigned idx = threadIdx.x; idx < total; idx += kThreads) {
+        for (unsigned idx = tid; idx < total; idx += nthr) {
             const unsigned c = fastdiv(idx, m_plane);
             const unsigned rem = idx - c * plane;
             const unsigned r = fastdiv(rem, m_nc);
@@ -104,7 +126,7 @@ __device__ __forceinline__ void stage_patch(float* __restrict__ sP, const float*
         const unsigned per_r = nc * C, total = nr * per_r;
         const unsigned m_row = magic_of(per_r);
         const float* g0 = src + (((size_t) img * h + r0) * w + c0) * C;
-        for (unsigned idx = threadIdx.x; idx < total; idx += kThreads) {
+        for (unsigned idx = tid; idx < total; idx += nthr) {
             const unsigned r = fastdiv(idx, m_row);
             const unsigned rem = idx - r * per_r;
             cp_async_f32(sP + r * pcols * C + rem, g0 + (size_t) r * w * C + rem);
@@ -112,93 +134,128 @@ __device__ __forceinline__ void stage_patch(float* __restrict__ sP, const float*
     }
 }
 
-// ---- (2) materialise one tensor (C channels) of the tile -------------------------------------
-// sP: HWC patch in shared memory with origin (pr0, pc0) and `pcols` columns per row.
-// Every thread owns float4 columns of the tile's output rows: 4 consecutive (x, c) entries, for
-// which the horizontal interpolation is done once per stride-8 row and each output row costs
-// four FMAs and one 16-byte store.
-// Columns col_begin, col_begin + col_step, ... of the tile row are handled by the calling thread (the
-// whole block strides by kThreads; a single warp takes one 32-column chunk).
+// ---- (2) materialise heat_mat / paf_mat through the TMA engine --------------------------------
+// cp.async.bulk (UBLKCP) shared -> global: a chunk of [<= 8 output rows][kChunkCols float4 columns]
+// is written to a shared-memory buffer by the fill warps (a thread owns a float4 column = 4
+// consecutive (x, c) entries of an output row: the horizontal interpolation is done once per
+// stride-8 row, then each output row costs four FMAs and one 16-byte shared-memory store), then one
+// lane per fill warp hands one row each (kChunkCols x 16 B = 4 KB contiguous in HBM) to the TMA
+// engine.  Stores never occupy the warps' scoreboards or LSU queues: the engine drains the buffers
+// while the CTA stages, smooths and does the NMS.  tools/bulk_store_probe.cu: this pattern alone
+// sustains 7.0-7.2 TB/s against 6.6-6.9 TB/s for per-thread st.global.cs.v4 on the same tiles.
+// A plain (non-tensor) bulk copy only needs 16-byte aligned addresses and sizes, which every row
+// segment of heat_mat / paf_mat has (W = 8w, so a row is 32*w*C bytes and a tile starts at
+// 32*i0*C bytes); no tensor map is involved.
+__device__ __forceinline__ void bulk_store_row(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned) __cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Called by the kFillThreads threads of the fill warps (named barrier BAR_FILL inside); t is the thread's
+// index within that group.  A thread owns kColsPerFillThread float4 columns of the chunk.  `phase`
+// counts the chunks emitted so far by this CTA (buffer ring position; lane 0 of every fill warp
+// commits one bulk group per chunk, so "all but the kStoreBufs-1 most recent groups have been read"
+// means the next buffer is free).
 template <int C>
 __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, int pr0, int pc0, int pcols,
-                                                 float* __restrict__ out_img, int h, int w, int m0, int tb,
-                                                 int i0, int twl, int col_begin, int col_step) {
+                                                      float* __restrict__ out_img, int h, int w, int m0, int tb, int i0,
+                                                      int twl, float4* __restrict__ sStore, int& phase, int t) {
+    constexpr int S = kColsPerFillThread;
     const int W = w * 8;
     const int X0 = i0 * 8;
-    const int row_f4 = twl * 2 * C;  // (8*twl*C)/4 float4 per tile row
+    const int row_f4 = twl * 2 * C;
     const size_t stride4 = (size_t) W * C / 4;
     const int prow = pcols * C;
-    for (int col = col_begin; col < row_f4; col += col_step) {
-        int off0[4], off1[4];
-        float tx[4];
+    const int lane = t & 31, fwarp = t >> 5;
+    const int Ystart = max(8 * m0 - 4, 0);
+    for (int c0 = 0; c0 < row_f4; c0 += kChunkCols) {
+        const int ncol = min(kChunkCols, row_f4 - c0);
+        bool valid[S];
+        int off0[S][4], off1[S][4];
+        float tx[S][4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int f = col * 4 + e;
-            const int xl = f / C;
-            const int c = f - xl * C;
-            int a, b;
-            bilin_coord(X0 + xl, w, a, b, tx[e]);
-            off0[e] = (a - pc0) * C + c;
-            off1[e] = (b - pc0) * C + c;
-        }
-        float top[4], bot[4], d[4];
-        auto load_row = [&](int j) {  // horizontal lerp of stride-8 row j (clamped by the caller)
-            const float* r = sP + (j - pr0) * prow;
+        for (int s = 0; s < S; s++) {
+            valid[s] = s * kFillThreads + t < ncol;
+            const int col = c0 + (valid[s] ? s * kFillThreads + t : 0);  // idle slots shadow column c0 (never stored)
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                top[e] = bot[e];
-                bot[e] = lerp1(r[off0[e]], r[off1[e]], tx[e]);
-                d[e] = __fsub_rn(bot[e], top[e]);
+                const int f = col * 4 + e;
+                const int xl = f / C;
+                const int c = f - xl * C;
+                int a, b;
+                bilin_coord(X0 + xl, w, a, b, tx[s][e]);
+                off0[s][e] = (a - pc0) * C + c;
+                off1[s][e] = (b - pc0) * C + c;
             }
-        };
-        // Rows k0 .. k0+NR-1 of the current pair (ty = (2k+1)/16).  All NR values are computed into
-        // distinct registers before the stores are issued: a store keeps its source registers busy
-        // until the LSU has accepted it, so reusing one float4 per row would allow only one store in
-        // flight per warp and starve the memory pipe (ncu: long-scoreboard stalls on the next FFMA).
-        auto store_rows = [&](float4*& dst, int k0, auto nr_tag) {
-            constexpr int NR = decltype(nr_tag)::value;
-            float4 v[NR];
+        }
+        float top[S][4], bot[S][4], d[S][4];
+        auto load_row = [&](int j) {  // horizontal lerp of stride-8 row j
+            const float* r = sP + (j - pr0) * prow;
 #pragma unroll
-            for (int k = 0; k < NR; k++) {
-                const float ty = (float) (2 * (k0 + k) + 1) * 0.0625f;
-                v[k].x = fmaf(ty, d[0], top[0]);
-                v[k].y = fmaf(ty, d[1], top[1]);
-                v[k].z = fmaf(ty, d[2], top[2]);
-                v[k].w = fmaf(ty, d[3], top[3]);
-            }
+            for (int s = 0; s < S; s++)
 #pragma unroll
-            for (int k = 0; k < NR; k++) __stcs(dst + (size_t) k * stride4, v[k]);
-            dst += (size_t) NR * stride4;
+                for (int e = 0; e < 4; e++) {
+                    top[s][e] = bot[s][e];
+                    bot[s][e] = lerp1(r[off0[s][e]], r[off1[s][e]], tx[s][e]);
+                    d[s][e] = __fsub_rn(bot[s][e], top[s][e]);
+                }
         };
-        auto store_range = [&](float4*& dst, auto k0_tag, auto n_tag) {  // n rows from k0, in batches of kRowBatch
+        float4* dst = reinterpret_cast<float4*>(out_img + ((size_t) Ystart * W + X0) * C) + c0;
+        auto emit = [&](auto k0_tag, auto n_tag) {  // rows k0 .. k0+n-1 of the current stride-8 row pair
             constexpr int K0 = decltype(k0_tag)::value, NN = decltype(n_tag)::value;
-            constexpr int RB = kRowBatch < NN ? kRowBatch : NN;
-            static_assert(NN % RB == 0, "row batch must divide 4");
+            float4* buf = sStore + (size_t) (phase % kStoreBufs) * kStoreBufF4;
+            if (lane == 0) bulk_wait_read<kStoreBufs - 1>();  // the copies that last read this buffer are done reading
+            bar_sync(BAR_FILL, kFillThreads);
 #pragma unroll
-            for (int b = 0; b < NN / RB; b++) store_rows(dst, K0 + b * RB, std::integral_constant<int, RB>{});
+            for (int s = 0; s < S; s++) {
+                if (!valid[s]) continue;
+#pragma unroll
+                for (int k = 0; k < NN; k++) {
+                    const float ty = (float) (2 * (K0 + k) + 1) * 0.0625f;
+                    float4 v;
+                    v.x = fmaf(ty, d[s][0], top[s][0]);
+                    v.y = fmaf(ty, d[s][1], top[s][1]);
+                    v.z = fmaf(ty, d[s][2], top[s][2]);
+                    v.w = fmaf(ty, d[s][3], top[s][3]);
+                    buf[k * kChunkCols + s * kFillThreads + t] = v;
+                }
+            }
+            fence_proxy_async();  // generic-proxy writes above -> visible to the async proxy (TMA)
+            bar_sync(BAR_FILL, kFillThreads);
+            if (lane == 0) {
+                for (int k = fwarp; k < NN; k += kFillWarps) bulk_store_row(dst + (size_t) k * stride4, buf + k * kChunkCols, ncol * 16);
+                bulk_commit();
+            }
+            dst += (size_t) NN * stride4;
+            phase++;
         };
 #pragma unroll
-        for (int e = 0; e < 4; e++) bot[e] = 0.f;
+        for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) bot[s][e] = 0.f;
+        using I0 = std::integral_constant<int, 0>;
+        using I4 = std::integral_constant<int, 4>;
+        using I8 = std::integral_constant<int, 8>;
         // The tile materialises the rows of the stride-8 row PAIRS (m0-1, m0) .. (m0+tb-2, m0+tb-1),
         // i.e. rows 8*m0-4 .. 8*(m0+tb)-5: each pair is complete (8 rows, one horizontal lerp per
         // stride-8 row).  The clamped half pairs at the top and bottom of the image belong to the
         // first and last tile.
         load_row(max(m0 - 1, 0));
-        const int Ystart = max(8 * m0 - 4, 0);
-        float4* dst = reinterpret_cast<float4*>(out_img + ((size_t) Ystart * W + X0) * C) + col;
         load_row(m0);
-        using I0 = std::integral_constant<int, 0>;
-        using I4 = std::integral_constant<int, 4>;
-        using I8 = std::integral_constant<int, 8>;
-        if (m0 == 0) store_range(dst, I4{}, I4{});  // pair (-1, 0): only its lower half exists (rows 0..3)
-        else store_range(dst, I0{}, I8{});
+        if (m0 == 0) emit(I4{}, I4{});
+        else emit(I0{}, I8{});
         for (int q = 1; q < tb; q++) {
             load_row(m0 + q);
-            store_range(dst, I0{}, I8{});
+            emit(I0{}, I8{});
         }
-        if (m0 + tb == h) {  // last tile: pair (h-1, h): only its upper half exists (rows 8h-4..8h-1)
+        if (m0 + tb == h) {
             load_row(h - 1);
-            store_range(dst, I0{}, I4{});
+            emit(I0{}, I4{});
         }
     }
 }
@@ -273,73 +330,42 @@ __device__ __forceinline__ TileGeom tile_geom(const DenseParams& p, int tile_x, 
 struct TileSmem {
     float* heat;    // [kHeatRows][tile_wl + 6][19]
     float* paf;     // [kPafRows][tile_wl + 2][38]
+    float4* store;  // [kStoreBufs][8][kChunkCols] float4 (materialising kernel only)
 };
 
-// Request a tile's stride-8 patches.  The PAF patch (2/3 of the stores depend on it) goes first and
-// the heat patch second, as two cp.async groups.
-template <bool kMat>
-__device__ __forceinline__ void issue_stage(const DenseParams& p, const TileGeom& g, const TileSmem& sm) {
-    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
-    if (kMat) {
-        stage_patch<EKP_PAF_CH>(sm.paf, p.paf, p.layout, g.img, p.h, p.w, g.pr0, g.pr1, g.pc0, g.pc1, pcols);
-        stage_commit();
+// Everything a tile's threads share besides the patches.
+struct TileCtl {
+    float* colmax;            // [tile_wl + 6][19] max(0, column maximum over the staged heat rows)
+    const float* taps;        // [8][8] interior taps by phase (copy of cTapsInterior for per-lane indexing)
+    unsigned short* list;     // (part, strip) tasks that survive the early-out
+    int* num_active;
+    int* next_task;
+};
+
+// per (column, channel) maximum of the staged heat samples, for the early-out below
+__device__ __forceinline__ void build_colmax(const TileGeom& g, const float* sHeat, int hcols, float* sColMax, int tid, int nthr) {
+    const int ncolc = (g.hc1 - g.hc0 + 1) * EKP_HEAT_CH, nrow = g.hr1 - g.hr0 + 1;
+    for (int idx = tid; idx < ncolc; idx += nthr) {
+        float mx = 0.f;
+        for (int r = 0; r < nrow; r++) mx = fmaxf(mx, sHeat[r * hcols * EKP_HEAT_CH + idx]);
+        sColMax[idx] = mx;
     }
-    stage_patch<EKP_HEAT_CH>(sm.heat, p.heat, p.layout, g.img, p.h, p.w, g.hr0, g.hr1, g.hc0, g.hc1, hcols);
-    stage_commit();
 }
 
-// Everything after the patches were requested (they are the two most recent cp.async groups):
-// paf_mat is streamed out while the heat patch is still in flight.
-template <bool kMat, bool kDebug>
-__device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeom& g, const TileSmem& sm, float* sColMax,
-                                             const float* sTaps, unsigned short* sList, int* sNumActive, int* sNextTask,
-                                             int* sNextChunk) {
-    const int img = g.img, m0 = g.m0, i0 = g.i0, twl = g.twl, tb = g.tb;
-    const int hr0 = g.hr0, hr1 = g.hr1, hc0 = g.hc0, hc1 = g.hc1, pr0 = g.pr0, pc0 = g.pc0;
-    const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
-    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
-    float* sHeat = sm.heat;
-    float* sPaf = sm.paf;
-
-    if (kMat) {
-        stage_wait<1>();
-        __syncthreads();
-        materialise_tile<EKP_PAF_CH>(sPaf, pr0, pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0, twl,
-                                      threadIdx.x, kThreads);
-    }
-    stage_wait<0>();
-    __syncthreads();
-    if (!kDebug) {  // per (column, channel) maximum of the staged heat samples, for the early-out below
-        const int ncolc = (hc1 - hc0 + 1) * EKP_HEAT_CH, nrow = hr1 - hr0 + 1;
-        for (int idx = threadIdx.x; idx < ncolc; idx += kThreads) {
-            float mx = 0.f;
-            for (int r = 0; r < nrow; r++) mx = fmaxf(mx, sHeat[r * hcols * EKP_HEAT_CH + idx]);
-            sColMax[idx] = mx;
-        }
-    }
-    if (!kDebug) __syncthreads();  // sColMax complete
-
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler too
-    const int TW = 8 * twl, X0 = 8 * i0;
+// ---- exact early-out, decided once per (part, strip) by one thread each -------------------------
+// All taps are >= 0 and sum to 1 (checked on the host), so every smoothed value a strip can
+// produce is a convex combination of the staged stride-8 samples in columns
+// [bx(first lane), bx(last lane) + 4]: if their maximum (sColMax, over all staged rows) is below
+// the threshold by more than the rounding slack of ten float operations, no pixel there can
+// pass `S > thr`, hence no peak, and the strip is never visited.  Survivors go to a compact
+// list that the warps then share evenly.
+template <bool kDebug>
+__device__ __forceinline__ void build_task_list(const DenseParams& p, const TileGeom& g, const TileCtl& ctl, int tid, int nthr) {
+    const int w = p.w, W = 8 * w, TW = 8 * g.twl, X0 = 8 * g.i0;
     const int nstrips = (TW + 29) / 30;
     const unsigned m_strips = magic_of(nstrips);
-    const float NEG_INF = __int_as_float(0xff800000);
-    const int rstride = hcols * EKP_HEAT_CH;
-    PeakSink sink;
-    sink.raw = p.raw + (size_t) img * p.raw_cap;
-    sink.count = p.raw_count + img;
-    sink.cap = p.raw_cap;
-
-    // ---- exact early-out, decided once per (part, strip) by one thread each -------------------
-    // All taps are >= 0 and sum to 1 (checked on the host), so every smoothed value a strip can
-    // produce is a convex combination of the staged stride-8 samples in columns
-    // [bx(first lane), bx(last lane) + 4]: if their maximum (sColMax, over all staged rows) is below
-    // the threshold by more than the rounding slack of ten float operations, no pixel there can
-    // pass `S > thr`, hence no peak, and the strip is never visited.  Survivors go to a compact
-    // list that the warps then share evenly.
     const int ntask = EKP_NUM_PART * nstrips;
-    for (int t = threadIdx.x; t < ntask; t += kThreads) {
+    for (int t = tid; t < ntask; t += nthr) {
         const int c = (int) fastdiv(t, m_strips);
         const int strip = t - c * nstrips;
         bool active = kDebug || !(p.thr > 0.f);
@@ -348,151 +374,218 @@ __device__ __forceinline__ void process_tile(const DenseParams& p, const TileGeo
             const int xlo = min(max(Xa, 0), min(W - 1, X0 + TW)), xhi = min(max(Xa + 31, 0), min(W - 1, X0 + TW));
             const int c_lo = min(max((xlo >> 3) - 2, 0), w - 5), c_hi = min(max((xhi >> 3) - 2, 0), w - 5) + 4;
             float mx = 0.f;
-            for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, sColMax[(i - hc0) * EKP_HEAT_CH + c]);
+            for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, ctl.colmax[(i - g.hc0) * EKP_HEAT_CH + c]);
             active = mx > p.thr * 0.99999f;
         }
-        if (active) sList[atomicAdd(sNumActive, 1)] = (unsigned short) t;
+        if (active) ctl.list[atomicAdd(ctl.num_active, 1)] = (unsigned short) t;
     }
-    __syncthreads();
-    const int nactive = *sNumActive;
+}
 
-    // ---- heat_mat chunks and surviving NMS strips share the warps dynamically ---------------------
-    // Two warps start on the (ALU-bound) NMS strips, the others on the (store-bound) 32-column chunks
-    // of heat_mat; whoever runs out of its own kind takes the other.  Stores thus keep flowing while
-    // the smoothing runs, and heavy tiles (many people) are balanced across all warps.
-    const int nchunks = (kMat && p.heat_mat) ? (twl * 2 * EKP_HEAT_CH + 31) / 32 : 0;
-    const bool nms_first = warp < kNmsWarps;
-    for (;;) {
-        int kind = -1, item = 0;
-        if (lane == 0) {
-            if (nms_first) {
-                item = atomicAdd(sNextTask, 1);
-                if (item < nactive) kind = 0;
-                else { item = atomicAdd(sNextChunk, 1); if (item < nchunks) kind = 1; }
-            } else {
-                item = atomicAdd(sNextChunk, 1);
-                if (item < nchunks) kind = 1;
-                else { item = atomicAdd(sNextTask, 1); if (item < nactive) kind = 0; }
-            }
-        }
-        kind = __shfl_sync(0xffffffffu, kind, 0);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (kind < 0) break;
-        if (kind == 1) {
-            if (kMat)
-                materialise_tile<EKP_HEAT_CH>(sHeat, hr0, hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0, tb, i0,
-                                              twl, item * 32 + lane, 1 << 30);
-            continue;
-        }
-        const int task = sList[item];
-        const int c = (int) fastdiv(task, m_strips);
-        const int strip = task - c * nstrips;
-        const int X = X0 - 1 + 30 * strip + lane;
-        const bool inb = X >= 0 && X < W;
-        const bool out_lane = lane >= 1 && lane <= 30 && X < X0 + TW && X < W;
-        const int Xc = min(max(X, 0), min(W - 1, X0 + TW));  // lanes past the halo are never outputs
-        const int bx = min(max((Xc >> 3) - 2, 0), w - 5);
-        const float* colp = sHeat + (bx - hc0) * EKP_HEAT_CH + c - hr0 * rstride;
+// One (part, 30-column strip) task, by one warp: smoothed map of the tile's rows (+ one halo row above and
+// below) in registers, 3x3 max NMS, peaks appended to the image's raw list.
+template <bool kDebug>
+__device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g, const float* sHeat, const float* sTaps, int task) {
+    const int img = g.img, m0 = g.m0, tb = g.tb;
+    const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
+    const int hcols = p.tile_wl + 6;
+    const int lane = threadIdx.x & 31;
+    const int TW = 8 * g.twl, X0 = 8 * g.i0;
+    const int nstrips = (TW + 29) / 30;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const int rstride = hcols * EKP_HEAT_CH;
+    PeakSink sink;
+    sink.raw = p.raw + (size_t) img * p.raw_cap;
+    sink.count = p.raw_count + img;
+    sink.cap = p.raw_cap;
 
-        // horizontal taps of this lane's column (only now: a skipped strip must not pay for the loads);
-        // interior columns take them from the phase table in shared memory, border columns from global
-        float4 axv;
-        float ax4;
-        if ((Xc >> 3) >= 2 && (Xc >> 3) <= w - 3) {
-            axv = *reinterpret_cast<const float4*>(sTaps + (Xc & 7) * 8);
-            ax4 = sTaps[(Xc & 7) * 8 + 4];
-        } else {
-            axv = __ldg(reinterpret_cast<const float4*>(p.ax + (size_t) Xc * 8));
-            ax4 = __ldg(p.ax + (size_t) Xc * 8 + 4);
-        }
-        auto trow = [&](int j) -> float {  // horizontal 5-tap pass on stride-8 row j
-            const float* s = colp + j * rstride;
-            float acc = __fmul_rn(axv.x, s[0]);
-            acc = fmaf(axv.y, s[EKP_HEAT_CH], acc);
-            acc = fmaf(axv.z, s[2 * EKP_HEAT_CH], acc);
-            acc = fmaf(axv.w, s[3 * EKP_HEAT_CH], acc);
-            acc = fmaf(ax4, s[4 * EKP_HEAT_CH], acc);
-            return acc;
-        };
-        float T0 = 0.f, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f;
-        int cur_wb = -100;
-        auto window = [&](int m) {  // make T0..T4 the horizontal results of row block m's window
-            const int wb = min(max(m - 2, 0), h - 5);
-            if (wb == cur_wb) return;
-            if (wb == cur_wb + 1) { T0 = T1; T1 = T2; T2 = T3; T3 = T4; T4 = trow(wb + 4); }
-            else { T0 = trow(wb); T1 = trow(wb + 1); T2 = trow(wb + 2); T3 = trow(wb + 3); T4 = trow(wb + 4); }
-            cur_wb = wb;
-        };
-        auto row_generic = [&](int Y) -> float {  // border rows: taps from the table in global memory
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.ay + (size_t) Y * 8));
-            const float a4 = __ldg(p.ay + (size_t) Y * 8 + 4);
-            float acc = __fmul_rn(a.x, T0);
-            acc = fmaf(a.y, T1, acc);
-            acc = fmaf(a.z, T2, acc);
-            acc = fmaf(a.w, T3, acc);
-            acc = fmaf(a4, T4, acc);
-            return acc;
-        };
-        auto debug_out = [&](int Y, float acc) {
-            if (kDebug && out_lane) p.smooth_out[(((size_t) img * H + Y) * W + X) * EKP_NUM_PART + c] = acc;
-        };
+    const int c = (int) fastdiv(task, magic_of(nstrips));
+    const int strip = task - c * nstrips;
+    const int X = X0 - 1 + 30 * strip + lane;
+    const bool inb = X >= 0 && X < W;
+    const bool out_lane = lane >= 1 && lane <= 30 && X < X0 + TW && X < W;
+    const int Xc = min(max(X, 0), min(W - 1, X0 + TW));  // lanes past the halo are never outputs
+    const int bx = min(max((Xc >> 3) - 2, 0), w - 5);
+    const float* colp = sHeat + (bx - g.hc0) * EKP_HEAT_CH + c - g.hr0 * rstride;
 
-        NmsState st;
-        st.hm2 = NEG_INF; st.hm1 = NEG_INF; st.s1 = NEG_INF;
-        const int Ytop = 8 * m0 - 1;
-        if (Ytop >= 0) {  // halo row above the tile: contributes its horizontal max only
-            window(m0 - 1);
-            const float acc = row_generic(Ytop);
-            nms_row(st, inb ? acc : NEG_INF, X, Ytop, false, p.thr, c, sink);
-            st.s1 = NEG_INF;  // not a tile-owned row: never reported from here
-        }
-        for (int b = 0; b < tb; b++) {
-            const int m = m0 + b;
-            window(m);
-            if (m >= 2 && m <= h - 3) {  // interior block: taps are immediates from the constant bank
+    // horizontal taps of this lane's column (only now: a skipped strip must not pay for the loads);
+    // interior columns take them from the phase table in shared memory, border columns from global
+    float4 axv;
+    float ax4;
+    if ((Xc >> 3) >= 2 && (Xc >> 3) <= w - 3) {
+        axv = *reinterpret_cast<const float4*>(sTaps + (Xc & 7) * 8);
+        ax4 = sTaps[(Xc & 7) * 8 + 4];
+    } else {
+        axv = __ldg(reinterpret_cast<const float4*>(p.ax + (size_t) Xc * 8));
+        ax4 = __ldg(p.ax + (size_t) Xc * 8 + 4);
+    }
+    auto trow = [&](int j) -> float {  // horizontal 5-tap pass on stride-8 row j
+        const float* s = colp + j * rstride;
+        float acc = __fmul_rn(axv.x, s[0]);
+        acc = fmaf(axv.y, s[EKP_HEAT_CH], acc);
+        acc = fmaf(axv.z, s[2 * EKP_HEAT_CH], acc);
+        acc = fmaf(axv.w, s[3 * EKP_HEAT_CH], acc);
+        acc = fmaf(ax4, s[4 * EKP_HEAT_CH], acc);
+        return acc;
+    };
+    float T0 = 0.f, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f;
+    int cur_wb = -100;
+    auto window = [&](int m) {  // make T0..T4 the horizontal results of row block m's window
+        const int wb = min(max(m - 2, 0), h - 5);
+        if (wb == cur_wb) return;
+        if (wb == cur_wb + 1) { T0 = T1; T1 = T2; T2 = T3; T3 = T4; T4 = trow(wb + 4); }
+        else { T0 = trow(wb); T1 = trow(wb + 1); T2 = trow(wb + 2); T3 = trow(wb + 3); T4 = trow(wb + 4); }
+        cur_wb = wb;
+    };
+    auto row_generic = [&](int Y) -> float {  // border rows: taps from the table in global memory
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.ay + (size_t) Y * 8));
+        const float a4 = __ldg(p.ay + (size_t) Y * 8 + 4);
+        float acc = __fmul_rn(a.x, T0);
+        acc = fmaf(a.y, T1, acc);
+        acc = fmaf(a.z, T2, acc);
+        acc = fmaf(a.w, T3, acc);
+        acc = fmaf(a4, T4, acc);
+        return acc;
+    };
+    auto debug_out = [&](int Y, float acc) {
+        if (kDebug && out_lane) p.smooth_out[(((size_t) img * H + Y) * W + X) * EKP_NUM_PART + c] = acc;
+    };
+
+    NmsState st;
+    st.hm2 = NEG_INF; st.hm1 = NEG_INF; st.s1 = NEG_INF;
+    const int Ytop = 8 * m0 - 1;
+    if (Ytop >= 0) {  // halo row above the tile: contributes its horizontal max only
+        window(m0 - 1);
+        const float acc = row_generic(Ytop);
+        nms_row(st, inb ? acc : NEG_INF, X, Ytop, false, p.thr, c, sink);
+        st.s1 = NEG_INF;  // not a tile-owned row: never reported from here
+    }
+    for (int b = 0; b < tb; b++) {
+        const int m = m0 + b;
+        window(m);
+        if (m >= 2 && m <= h - 3) {  // interior block: taps are immediates from the constant bank
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    float acc = __fmul_rn(cTapsInterior[k][0], T0);
-                    acc = fmaf(cTapsInterior[k][1], T1, acc);
-                    acc = fmaf(cTapsInterior[k][2], T2, acc);
-                    acc = fmaf(cTapsInterior[k][3], T3, acc);
-                    acc = fmaf(cTapsInterior[k][4], T4, acc);
-                    debug_out(8 * m + k, acc);
-                    nms_row(st, inb ? acc : NEG_INF, X, 8 * m + k, out_lane, p.thr, c, sink);
-                }
-            } else {
+            for (int k = 0; k < 8; k++) {
+                float acc = __fmul_rn(cTapsInterior[k][0], T0);
+                acc = fmaf(cTapsInterior[k][1], T1, acc);
+                acc = fmaf(cTapsInterior[k][2], T2, acc);
+                acc = fmaf(cTapsInterior[k][3], T3, acc);
+                acc = fmaf(cTapsInterior[k][4], T4, acc);
+                debug_out(8 * m + k, acc);
+                nms_row(st, inb ? acc : NEG_INF, X, 8 * m + k, out_lane, p.thr, c, sink);
+            }
+        } else {
 #pragma unroll 2
-                for (int k = 0; k < 8; k++) {
-                    const float acc = row_generic(8 * m + k);
-                    debug_out(8 * m + k, acc);
-                    nms_row(st, inb ? acc : NEG_INF, X, 8 * m + k, out_lane, p.thr, c, sink);
-                }
+            for (int k = 0; k < 8; k++) {
+                const float acc = row_generic(8 * m + k);
+                debug_out(8 * m + k, acc);
+                nms_row(st, inb ? acc : NEG_INF, X, 8 * m + k, out_lane, p.thr, c, sink);
             }
         }
-        const int Ybot = 8 * (m0 + tb);  // halo row below the tile (or the virtual row below the image)
-        float sb = NEG_INF;
-        if (Ybot < H) {
-            window(m0 + tb);
-            const float acc = row_generic(Ybot);
-            if (inb) sb = acc;
-        }
-        nms_row(st, sb, X, Ybot, out_lane, p.thr, c, sink);
+    }
+    const int Ybot = 8 * (m0 + tb);  // halo row below the tile (or the virtual row below the image)
+    float sb = NEG_INF;
+    if (Ybot < H) {
+        window(m0 + tb);
+        const float acc = row_generic(Ybot);
+        if (inb) sb = acc;
+    }
+    nms_row(st, sb, X, Ybot, out_lane, p.thr, c, sink);
+}
+
+// The calling warp takes surviving NMS tasks from the tile's list until none is left.
+template <bool kDebug>
+__device__ __forceinline__ void nms_task_loop(const DenseParams& p, const TileGeom& g, const float* sHeat, const TileCtl& ctl) {
+    const int nactive = *ctl.num_active;
+    for (;;) {
+        int item = 0;
+        if ((threadIdx.x & 31) == 0) item = atomicAdd(ctl.next_task, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nactive) break;
+        nms_task<kDebug>(p, g, sHeat, ctl.taps, ctl.list[item]);
+    }
+}
+
+// ---- one tile without materialisation (the lean and the debug kernel) ----------------------------------
+template <bool kDebug>
+__device__ __forceinline__ void process_tile_lean(const DenseParams& p, const TileGeom& g, const TileSmem& sm, const TileCtl& ctl) {
+    const int hcols = p.tile_wl + 6;
+    stage_patch<EKP_HEAT_CH>(sm.heat, p.heat, p.layout, g.img, p.h, p.w, g.hr0, g.hr1, g.hc0, g.hc1, hcols, threadIdx.x, kLeanThreads);
+    stage_commit();
+    stage_wait<0>();
+    __syncthreads();
+    if (!kDebug) {
+        build_colmax(g, sm.heat, hcols, ctl.colmax, threadIdx.x, kLeanThreads);
+        __syncthreads();
+    }
+    build_task_list<kDebug>(p, g, ctl, threadIdx.x, kLeanThreads);
+    __syncthreads();
+    nms_task_loop<kDebug>(p, g, sm.heat, ctl);
+}
+
+// ---- one tile with materialisation: TMA bulk stores, two warp roles -----------------------------------
+//   fill warps (kFillWarps): stage the PAF patch, turn it into paf_mat chunks in the store buffers and
+//       hand them to the TMA engine; then (once the other group has signalled BAR_HEAT_READY) the
+//       same for heat_mat; then help with the NMS tasks;
+//   NMS warps (the rest): stage the heat patch, build the early-out table and the task list, signal
+//       BAR_HEAT_READY, run the smoothing + NMS tasks.
+// The two groups only meet at that one barrier, so the smoothing of a tile runs underneath its stores
+// and the TMA queue of the SM (kStoreBufs chunks per resident CTA) never runs dry for long.
+__device__ __forceinline__ void process_tile_mat(const DenseParams& p, const TileGeom& g, const TileSmem& sm, const TileCtl& ctl) {
+    const int img = g.img, m0 = g.m0, i0 = g.i0, twl = g.twl, tb = g.tb;
+    const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
+    const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp < kFillWarps) {
+        const int t = threadIdx.x;
+        stage_patch<EKP_PAF_CH>(sm.paf, p.paf, p.layout, img, h, w, g.pr0, g.pr1, g.pc0, g.pc1, pcols, t, kFillThreads);
+        stage_commit();
+        stage_wait<0>();
+        bar_sync(BAR_FILL, kFillThreads);
+        int phase = 0;
+        materialise_tile<EKP_PAF_CH>(sm.paf, g.pr0, g.pc0, pcols, p.paf_mat + (size_t) img * H * W * EKP_PAF_CH, h, w, m0, tb, i0,
+                                          twl, sm.store, phase, t);
+        bar_sync(BAR_HEAT_READY, kMatThreads);  // heat patch staged, task list built
+        if (p.heat_mat)
+            materialise_tile<EKP_HEAT_CH>(sm.heat, g.hr0, g.hc0, hcols, p.heat_mat + (size_t) img * H * W * EKP_HEAT_CH, h, w, m0,
+                                               tb, i0, twl, sm.store, phase, t);
+        nms_task_loop<false>(p, g, sm.heat, ctl);
+        // shared memory must outlive the TMA engine's reads of the store buffers
+        if ((t & 31) == 0) bulk_wait_read<0>();
+    } else {
+        const int t = threadIdx.x - kFillThreads;
+        stage_patch<EKP_HEAT_CH>(sm.heat, p.heat, p.layout, img, h, w, g.hr0, g.hr1, g.hc0, g.hc1, hcols, t, kNmsThreads);
+        stage_commit();
+        stage_wait<0>();
+        bar_sync(BAR_NMS, kNmsThreads);
+        build_colmax(g, sm.heat, hcols, ctl.colmax, t, kNmsThreads);
+        bar_sync(BAR_NMS, kNmsThreads);
+        build_task_list<false>(p, g, ctl, t, kNmsThreads);
+        __threadfence_block();
+        bar_sync(BAR_NMS, kNmsThreads);     // list and count complete for this group ...
+        bar_arrive(BAR_HEAT_READY, kMatThreads);  // ... and published to the fill warps
+        nms_task_loop<false>(p, g, sm.heat, ctl);
     }
 }
 
 template <bool kMat, bool kDebug>
-__global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kernel(const DenseParams p) {
+__global__ void __launch_bounds__(kMat ? kMatThreads : kLeanThreads, kMat ? kMatBlocks : kLeanBlocks)
+dense_frontend_kernel(const DenseParams p) {
+    constexpr int kThreads = kMat ? kMatThreads : kLeanThreads;
     extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(16) float sTaps[64];  // interior taps by phase (copy of cTapsInterior for per-lane indexing)
-    __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];  // (part, strip) tasks that survive the early-out
-    __shared__ int sNumActive, sNextTask, sNextChunk;
+    __shared__ __align__(16) float sTaps[64];
+    __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];
+    __shared__ int sNumActive, sNextTask;
     if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
-    if (threadIdx.x == 0) { sNumActive = 0; sNextTask = 0; sNextChunk = 0; }
+    if (threadIdx.x == 0) { sNumActive = 0; sNextTask = 0; }
     const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
     TileSmem sm;
     sm.heat = smem;
     sm.paf = sm.heat + kHeatRows * hcols * EKP_HEAT_CH;
-    float* sColMax = sm.paf + kPafRows * pcols * EKP_PAF_CH;  // [hcols][19] max(0, column maximum over the staged rows)
+    TileCtl ctl;
+    ctl.colmax = sm.paf + (kMat ? kPafRows * pcols * EKP_PAF_CH : 0);  // no PAF patch without materialisation
+    ctl.taps = sTaps; ctl.list = sList; ctl.num_active = &sNumActive; ctl.next_task = &sNextTask;
+    // store buffers behind the patches, 128-byte aligned (the patches' size is a multiple of 4 bytes only)
+    sm.store = reinterpret_cast<float4*>(smem + (((size_t) (ctl.colmax + hcols * EKP_HEAT_CH - smem) + 31) & ~(size_t) 31));
     const TileGeom g = tile_geom(p, blockIdx.x, blockIdx.y, blockIdx.z);
     if (!kDebug) {
         // The first wave of CTAs pulls the WHOLE batch's stride-8 inputs into L2 (evict_last) in one
@@ -500,6 +593,7 @@ __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kerne
         // far more than their 36 MB (HBM read/write turnarounds): measured 0.415 -> 0.396 ms.
         const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         const unsigned ncta = gridDim.x * gridDim.y * gridDim.z;
+        constexpr unsigned kPrefetchCtas = 148u * (kMat ? kMatBlocks : kLeanBlocks);  // one resident wave on a B200
         const unsigned nfirst = ncta < kPrefetchCtas ? ncta : kPrefetchCtas;
         if (lin < nfirst) {
             const size_t heat_lines = ((size_t) p.n * EKP_HEAT_CH * p.h * p.w * 4 + 127) / 128;
@@ -510,13 +604,17 @@ __global__ void __launch_bounds__(kThreads, EKP_MIN_BLOCKS) dense_frontend_kerne
             }
         }
     }
-    issue_stage<kMat>(p, g, sm);
-    process_tile<kMat, kDebug>(p, g, sm, sColMax, sTaps, sList, &sNumActive, &sNextTask, &sNextChunk);
+    __syncthreads();  // sTaps and the task counters are initialised
+    if (kMat) process_tile_mat(p, g, sm, ctl);
+    else process_tile_lean<kDebug>(p, g, sm, ctl);
 }
 
-size_t dense_frontend_smem_bytes(int tile_wl) {
-    return sizeof(float) * ((size_t) kHeatRows * (tile_wl + 6) * EKP_HEAT_CH + (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH +
-                            (size_t) (tile_wl + 6) * EKP_HEAT_CH);
+size_t dense_frontend_smem_bytes(int tile_wl, bool materialise) {
+    size_t floats = (size_t) kHeatRows * (tile_wl + 6) * EKP_HEAT_CH + (size_t) (tile_wl + 6) * EKP_HEAT_CH;
+    if (!materialise) return sizeof(float) * floats;
+    floats += (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH;
+    floats = (floats + 31) & ~(size_t) 31;
+    return sizeof(float) * floats + sizeof(float4) * (size_t) kStoreBufs * kStoreBufF4;
 }
 // choose the stride-8 tile width: <= kMaxTwl columns, tiles of (nearly) equal width
 int dense_frontend_tile_wl(int w) {
@@ -526,22 +624,23 @@ int dense_frontend_tile_wl(int w) {
 
 // per device, once (ekp_create): allow the largest tile's dynamic shared memory
 cudaError_t configure_dense_frontend() {
-    const int smem = (int) dense_frontend_smem_bytes(kMaxTwl);
-    cudaError_t e = cudaFuncSetAttribute(dense_frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int) dense_frontend_smem_bytes(kMaxTwl, false);
+    cudaError_t e = cudaFuncSetAttribute(dense_frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) dense_frontend_smem_bytes(kMaxTwl, true));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_frontend_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_frontend_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
 }
 
-// One CTA per tile.  (A persistent variant -- resident CTAs pulling tiles from a counter with the
-// next tile's patches prefetched into a double buffer -- was measured 7 % SLOWER on B200, 0.442 vs
-// 0.412 ms: it loses the PAF-first overlap and runs the CTAs in lock-step; see profiles/README.md.)
+// One CTA per tile.  (With per-thread stores, a persistent variant -- resident CTAs pulling tiles from a
+// counter with the next tile's patches prefetched into a double buffer -- was measured 7 % SLOWER on
+// B200, 0.442 vs 0.412 ms; see profiles/README.md.)
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
-    const size_t smem = dense_frontend_smem_bytes(p.tile_wl);
+    const size_t smem = dense_frontend_smem_bytes(p.tile_wl, p.paf_mat != nullptr && !p.smooth_out);
     dim3 grid((p.w + p.tile_wl - 1) / p.tile_wl, (p.h + kTB - 1) / kTB, p.n);
-    if (p.smooth_out) dense_frontend_kernel<false, true><<<grid, kThreads, smem, stream>>>(p);
-    else if (p.paf_mat) dense_frontend_kernel<true, false><<<grid, kThreads, smem, stream>>>(p);
-    else dense_frontend_kernel<false, false><<<grid, kThreads, smem, stream>>>(p);
+    if (p.smooth_out) dense_frontend_kernel<false, true><<<grid, kLeanThreads, smem, stream>>>(p);
+    else if (p.paf_mat) dense_frontend_kernel<true, false><<<grid, kMatThreads, smem, stream>>>(p);
+    else dense_frontend_kernel<false, false><<<grid, kLeanThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
