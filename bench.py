@@ -41,13 +41,14 @@ BATCH = 64            # images per GPU per step (configs[1])
 H_LO, W_LO = 46, 54   # stride-8 map of a 368x432 image
 PEOPLE = (1, 6)
 INPUT_SETS = 4        # distinct input batches rotated between steps
+N_CTX = int(os.environ.get("EKP_BENCH_CONTEXTS", "4"))   # contexts / CUDA streams the steps rotate over
 ALGO_BYTES_PER_IMAGE = 4 * H_LO * W_LO * 57 + 4 * (8 * H_LO) * (8 * W_LO) * 57   # 36,812,880
 CONFIG = {
     "workload": "configs[1]: batch 64 synthetic heat(19ch)/PAF(38ch) at 46x54 stride-8 (368x432), "
                 "dense front-end materialising heat_mat/paf_mat + PAF scoring + assembly",
     "batch_per_gpu": BATCH, "shape": "368x432", "people_per_image": "1-6", "frontend": "dense",
     "materialize": True,
-    "pipelining": "2 contexts on 2 CUDA streams alternate between steps (stages 4-5 of one batch overlap the "
+    "pipelining": f"{N_CTX} contexts on {N_CTX} CUDA streams take the steps in turn (stages 4-5 of one batch overlap the "
                   "front-end kernel of the next)",
     "l2": "every step writes 2.3 GB of operator-surface tensors (>> 126 MB L2); inputs rotate over "
           f"{INPUT_SETS} distinct batches",
@@ -259,13 +260,14 @@ def run_ours(args, rank, local_rank, world):
         sets_dev.append((ht.to(dev), pt.to(dev)))
         if s == 0:
             sample_imgs = hwc_images(heat, paf, 8)
-    # Two contexts on two streams alternate between steps, so the small latency-bound kernels of
-    # stages 4-5 of batch i run under the HBM-bound front-end kernel of batch i+1.
+    # N_CTX contexts on N_CTX streams take the steps in turn, so the small latency-bound kernels of
+    # stages 4-5 of batch i run under the HBM-bound front-end kernel of batch i+1 (and with three, the
+    # front-end of batch i+2 does not queue behind stages 4-5 of batch i on the same stream).
     mk = lambda: ek.PostProcessor(device=local_rank, max_batch=BATCH, max_h=H_LO, max_w=W_LO, max_peaks=1024, max_humans=32)
-    pps = [mk(), mk()]
+    pps = [mk() for _ in range(N_CTX)]
     pp = pps[0]
     stream = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(N_CTX)]
 
     def barrier():
         if world > 1:
@@ -274,7 +276,7 @@ def run_ours(args, rank, local_rank, world):
 
     def step_device(i):
         hd, pd = sets_dev[i % INPUT_SETS]
-        pps[i % 2].run(hd, pd, layout="nchw", frontend="dense", materialize=True, stream=streams[i % 2])
+        pps[i % N_CTX].run(hd, pd, layout="nchw", frontend="dense", materialize=True, stream=streams[i % N_CTX])
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -300,12 +302,11 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     clocks.region(False)
     ms = ev0.elapsed_time(ev1)
-    res = pps[(args.steps - 1) % 2].results()
+    res = pps[(args.steps - 1) % N_CTX].results()
     launches = sum(p_.kernel_launches() for p_ in pps) - launches0
-    st0, runs0 = pps[0].stage_times()
-    st1, runs1 = pps[1].stage_times() if args.steps > 1 else (st0, 0)
-    stage_runs = runs0 + runs1
-    stage_ms = {k: (st0[k] * runs0 + st1[k] * runs1) / max(stage_runs, 1) for k in st0}
+    per_ctx = [p_.stage_times() for p_ in pps[:max(1, min(N_CTX, args.steps))]]
+    stage_runs = sum(r for _, r in per_ctx)
+    stage_ms = {k: sum(st[k] * r for st, r in per_ctx) / max(stage_runs, 1) for k in per_ctx[0][0]}
     for p_ in pps:
         p_.set_timing(False)
     total_humans = int(res["num_humans"].sum())
@@ -323,15 +324,15 @@ def run_ours(args, rank, local_rank, world):
     # ---- context numbers (not the headline): the same batch without materialising the operator-surface
     #      tensors, and through the reference's own front-end (stride-8 NMS + bicubic refinement)
     def variant(frontend, materialize, steps=100):
-        for i in range(4):
-            pps[i % 2].run(*sets_dev[i % INPUT_SETS], layout="nchw", frontend=frontend, materialize=materialize, stream=streams[i % 2])
+        for i in range(2 * N_CTX):
+            pps[i % N_CTX].run(*sets_dev[i % INPUT_SETS], layout="nchw", frontend=frontend, materialize=materialize, stream=streams[i % N_CTX])
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         for s_ in streams:
             s_.wait_stream(stream)
         for i in range(steps):
-            pps[i % 2].run(*sets_dev[i % INPUT_SETS], layout="nchw", frontend=frontend, materialize=materialize, stream=streams[i % 2])
+            pps[i % N_CTX].run(*sets_dev[i % INPUT_SETS], layout="nchw", frontend=frontend, materialize=materialize, stream=streams[i % N_CTX])
         for s_ in streams:
             stream.wait_stream(s_)
         b.record(stream)
@@ -342,24 +343,24 @@ def run_ours(args, rank, local_rank, world):
                 "reference_frontend_no_materialise_images_per_s": variant("reference", False)}
 
     # ---- e2e: host buffers through the C ABI, copies in the timed region ---------------------------
-    # A stream of batches the way a caller would drive it: two contexts on two streams, so the H2D
+    # A stream of batches the way a caller would drive it: N_CTX contexts on N_CTX streams, so the H2D
     # copy of batch i+1 overlaps the kernels of batch i; EVERY step's inputs come from pinned host
     # memory and EVERY step's result tables are read back on the host inside the timed region.
     def e2e_submit(i):
         hp, ppin = sets_pin[i % INPUT_SETS]
-        pps[i % 2].run(hp, ppin, layout="nchw", frontend="dense", materialize=True, stream=streams[i % 2])
+        pps[i % N_CTX].run(hp, ppin, layout="nchw", frontend="dense", materialize=True, stream=streams[i % N_CTX])
 
     def e2e_loop(steps):
         got = None
         for i in range(steps):
-            if i >= 2:
-                got = pps[i % 2].human_tables()      # results of step i-2 (waits for it)
+            if i >= N_CTX:
+                got = pps[i % N_CTX].human_tables()      # results of step i-N_CTX (waits for it)
             e2e_submit(i)
-        for i in range(max(steps - 2, 0), steps):
-            got = pps[i % 2].human_tables()
+        for i in range(max(steps - N_CTX, 0), steps):
+            got = pps[i % N_CTX].human_tables()
         return got
 
-    e2e_loop(4)
+    e2e_loop(2 * N_CTX)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -416,7 +417,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": images / (max(e2e_ms, e2e_wall_ms) / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "device_ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps,
-                    "api": "ekp_postprocess_host + ekp_results_humans (pinned host buffers; 2 contexts / 2 streams "
+                    "api": f"ekp_postprocess_host + ekp_results_humans (pinned host buffers; {N_CTX} contexts / {N_CTX} streams "
                            "so the H2D of one batch overlaps the kernels of the previous one)"},
             "gpu_launches": int(launches), "clocks": clk, "humans_found_last_step": total_humans,
             "variants_per_gpu": variants,
