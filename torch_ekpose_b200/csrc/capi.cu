@@ -35,7 +35,7 @@ cudaError_t configure_assemble(int max_humans, int max_peaks);
 cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,
                             int max_humans, int n, const unsigned* overflow, unsigned char* records, const ResultLayout& lay,
                             cudaStream_t stream);
-cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, cudaStream_t stream);
+cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned* scratch, cudaStream_t stream);
 cudaError_t launch_preprocess(const unsigned char* src, float* out, const int* xofs, const short* ialpha, const int* yofs,
                               const short* ibeta, int n, int sh, int sw, int rh, int rw, int ph, int pw, int mode,
                               cudaStream_t stream);
@@ -443,8 +443,10 @@ extern "C" int ekp_results_humans(ekp_ctx* c, int* num_humans, ekp_peak* parts, 
 extern "C" int ekp_debug_std_sort(ekp_ctx* c, float* scores_dev, unsigned* tags_dev, int n, void* stream) {
     if (!c || n < 0 || (n > 0 && (!scores_dev || !tags_dev))) return fail(EKP_ERR_ARG, "ekp_debug_std_sort: bad arguments");
     if (n == 0) return EKP_OK;
+    if (n > 16384) return fail(EKP_ERR_ARG, "ekp_debug_std_sort: n %d > 16384", n);
     CU(cudaSetDevice(c->device));
-    CU(launch_debug_std_sort(scores_dev, tags_dev, n, (cudaStream_t) stream));
+    // scratch for the replay's range list: the connection buffer (>= 19 * 256 * 16 bytes, idle between runs)
+    CU(launch_debug_std_sort(scores_dev, tags_dev, n, reinterpret_cast<unsigned*>(c->conns), (cudaStream_t) stream));
     c->launches += 1;
     return EKP_OK;
 }

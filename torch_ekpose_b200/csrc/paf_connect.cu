@@ -10,6 +10,12 @@
 //  * the ten sample scores are accumulated in sample order by the thread that owns the pair;
 //  * candidates are compacted in the reference's push order (a outer, b inner) with an ordered
 //    ballot/prefix compaction;
+//  * two-pass scoring: a pair needs criterion1 > 6 of its 10 samples above 0.05 (pafprocess.cpp:80,85), so a
+//    pair whose four MIDDLE samples (i = 3..6, the most discriminative ones: the ends lie on the true limbs
+//    of a and b) all fail can never pass.  Pass 1 evaluates only those four (same float operations as the
+//    full evaluation, so the test is exact) and keeps the survivors in pair order; pass 2 runs the full,
+//    unmodified evaluation on the survivors only.  In crowded scenes > 90 % of the pairs end in pass 1;
+//    the gathers are what the kernel is bound by (fully divergent loads: one L1 tag per lane per load);
 //  * sorting (pafprocess.cpp:97): the reference's result depends on HOW std::sort permutes equal
 //    scores.  For n <= 16 libstdc++ runs a stable insertion sort, and without ties the order is
 //    unique, so all threads rank the candidates in parallel (stable) and look for ties; only when
@@ -20,37 +26,96 @@
 
 namespace ekp {
 
-constexpr int kConnThreads = 128;
+#ifndef EKP_CONN_THREADS
+#define EKP_CONN_THREADS 128
+#endif
+constexpr int kConnThreads = EKP_CONN_THREADS;
+constexpr int kSurvWindow = 2048;  // pairs per pass-1 window (survivor list capacity)
 
 struct Sample2 { float x, y; };
 
+// Both channels of a limb at one position of a channel-last tensor.  Every limb's two PAF channels are
+// adjacent (ch2 == ch1 + 1, ch1 even: pafprocess.h:16-19), so when the channel count is even and the base
+// 8-byte aligned (kVec2) one 8-byte load fetches both -- half the gathers.
+template <bool kVec2>
+__device__ __forceinline__ Sample2 pair_at(const float* q, int ch1, int ch2) {
+    Sample2 r;
+    if (kVec2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(q + ch1));
+        r.x = v.x; r.y = v.y;
+    } else {
+        r.x = __ldg(q + ch1);
+        r.y = __ldg(q + ch2);
+    }
+    return r;
+}
+
+template <bool kVec2>
 __device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int ly, int lx, int ch1, int ch2) {
     Sample2 r;
     lx = min(max(lx, 0), s.W - 1);  // memory safety only: valid peaks never sample outside
     ly = min(max(ly, 0), s.H - 1);
     if (s.mode == PAF_FULL_HWC) {
-        const float* q = s.ptr + (((size_t) img * s.H + ly) * s.W + lx) * s.C;
-        r.x = __ldg(q + ch1);
-        r.y = __ldg(q + ch2);
+        r = pair_at<kVec2>(s.ptr + (((size_t) img * s.H + ly) * s.W + lx) * s.C, ch1, ch2);
     } else if (s.mode == PAF_LO_NEAREST) {
-        r.x = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, ly >> 3, lx >> 3);
-        r.y = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, ly >> 3, lx >> 3);
+        if (s.layout == EKP_LAYOUT_NHWC) {
+            r = pair_at<kVec2>(s.ptr + (((size_t) img * s.h + (ly >> 3)) * s.w + (lx >> 3)) * s.C, ch1, ch2);
+        } else {
+            r.x = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, ly >> 3, lx >> 3);
+            r.y = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, ly >> 3, lx >> 3);
+        }
     } else {  // identical arithmetic to materialise_tile (dense_frontend.cu)
         int i0, i1, j0, j1;
         float tx, ty;
         bilin_coord(lx, s.w, i0, i1, tx);
         bilin_coord(ly, s.h, j0, j1, ty);
-        float top = lerp1(lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j0, i0), lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j0, i1), tx);
-        float bot = lerp1(lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j1, i0), lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j1, i1), tx);
-        r.x = lerp1(top, bot, ty);
-        top = lerp1(lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j0, i0), lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j0, i1), tx);
-        bot = lerp1(lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j1, i0), lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j1, i1), tx);
-        r.y = lerp1(top, bot, ty);
+        Sample2 c00, c01, c10, c11;
+        if (s.layout == EKP_LAYOUT_NHWC) {
+            const float* b0 = s.ptr + ((size_t) img * s.h + j0) * s.w * s.C;
+            const float* b1 = s.ptr + ((size_t) img * s.h + j1) * s.w * s.C;
+            c00 = pair_at<kVec2>(b0 + (size_t) i0 * s.C, ch1, ch2); c01 = pair_at<kVec2>(b0 + (size_t) i1 * s.C, ch1, ch2);
+            c10 = pair_at<kVec2>(b1 + (size_t) i0 * s.C, ch1, ch2); c11 = pair_at<kVec2>(b1 + (size_t) i1 * s.C, ch1, ch2);
+        } else {
+            c00.x = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j0, i0); c01.x = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j0, i1);
+            c10.x = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j1, i0); c11.x = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch1, j1, i1);
+            c00.y = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j0, i0); c01.y = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j0, i1);
+            c10.y = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j1, i0); c11.y = lo_at(s.ptr, s.layout, img, s.C, s.h, s.w, ch2, j1, i1);
+        }
+        r.x = lerp1(lerp1(c00.x, c01.x, tx), lerp1(c10.x, c11.x, tx), ty);
+        r.y = lerp1(lerp1(c00.y, c01.y, tx), lerp1(c10.y, c11.y, tx), ty);
     }
     return r;
 }
 
+// Pass 1: can the pair still satisfy criterion1 > 6 (pafprocess.cpp:80,85)?  Evaluates samples 3..6 with the
+// float operations of score_pair; false when all four are <= 0.05 (then at most 6 of 10 can pass) or the
+// two peaks coincide (:66).
+template <bool kVec2>
+__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1, int ch2) {
+    const int dxi = b.x - a.x, dyi = b.y - a.y;
+    float vx = (float) dxi, vy = (float) dyi;
+    const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+    if ((double) norm < 1e-12) return false;
+    vx = __fdiv_rn(vx, norm);
+    vy = __fdiv_rn(vy, norm);
+    const float step_x = __fdiv_rn((float) dxi, 10.0f);
+    const float step_y = __fdiv_rn((float) dyi, 10.0f);
+    Sample2 sv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = 3 + k;
+        const int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);
+        const int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
+        sv[k] = paf_sample<kVec2>(paf, img, ly, lx, ch1, ch2);
+    }
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) any |= __fadd_rn(__fmul_rn(vx, sv[k].x), __fmul_rn(vy, sv[k].y)) > 0.05f;
+    return any;
+}
+
 // pafprocess.cpp:59-94 for one (a, b) pair.  Returns true when the pair becomes a candidate.
+template <bool kVec2>
 __device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1,
                                            int ch2, int h1, float& criterion2) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
@@ -69,7 +134,7 @@ __device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b,
     }
     Sample2 sv[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) sv[i] = paf_sample(paf, img, ly[i], lx[i], ch1, ch2);  // independent gathers in flight
+    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kVec2>(paf, img, ly[i], lx[i], ch1, ch2);  // independent gathers in flight
     float scores = 0.0f;
     int criterion1 = 0;
 #pragma unroll
@@ -138,35 +203,11 @@ __device__ void sort_heapsort(const CandArray& A, int first, int last) {  // __p
     }
 }
 // ---- the same algorithm executed by ONE WARP ---------------------------------------------------
-// Control flow, comparisons and element moves are exactly libstdc++'s (same order), but every scan
-// ("advance while comp holds") inspects 32 elements per step with a ballot and every shift of the
-// insertion sort moves its elements in parallel.  All 32 lanes call these with identical arguments.
+// Control flow, comparisons and element moves of the quicksort phase are exactly libstdc++'s (same
+// order), but every scan ("advance while comp holds") inspects 32 elements per step with a ballot; the
+// final insertion sort runs one lane per independent range (see std_sort_desc).  All 32 lanes call
+// these with identical arguments.
 __device__ __forceinline__ int lead_true(unsigned m) { return m == 0xffffffffu ? 32 : __ffs(~m) - 1; }
-
-// __unguarded_linear_insert(i) / the guarded branch of __insertion_sort: move element i left past
-// every element it is greater than (`lower` = lowest index that may be inspected).
-__device__ void warp_linear_insert(const CandArray& A, int i, int lower) {
-    const int lane = threadIdx.x & 31;
-    const Cand val = A.get(i);
-    int d = 0;  // number of elements val has to pass
-    for (;;) {
-        const int idx = i - 1 - d - lane;
-        const int run = lead_true(__ballot_sync(0xffffffffu, idx >= lower && val.s > A.s[idx]));
-        d += run;
-        if (run < 32) break;
-    }
-    if (d == 0) return;
-    for (int c0 = 0; c0 < d; c0 += 32) {  // shift [i-d, i-1] up by one, topmost chunk first
-        const int k = c0 + lane;
-        Cand t;
-        if (k < d) t = A.get(i - 1 - k);
-        __syncwarp();
-        if (k < d) A.set(i - k, t);
-        __syncwarp();
-    }
-    if (lane == 0) A.set(i - d, val);
-    __syncwarp();
-}
 
 // __unguarded_partition(lo, hi, pivot)
 __device__ int warp_partition(const CandArray& A, int lo, int hi, float pivot, int n) {
@@ -192,23 +233,26 @@ __device__ int warp_partition(const CandArray& A, int lo, int hi, float pivot, i
     }
 }
 
-__device__ void std_sort_desc(const CandArray& A, int n) {
+// `blocks`: scratch for one packed (first << 16 | last) entry per final range, >= n entries (n <= 65535).
+__device__ void std_sort_desc(const CandArray& A, int n, unsigned* blocks) {
     if (n <= 0) return;
     const int lane = threadIdx.x & 31;
     // __introsort_loop with an explicit stack: the recursion only ever touches disjoint ranges,
     // so the order in which they are finished does not change the result.
     int stk_first[48], stk_last[48], stk_depth[48];
-    int sp = 0;
+    int sp = 0, nblk = 0;
     int lg = 0;
     for (int v = n; v > 1; v >>= 1) lg++;
     stk_first[sp] = 0; stk_last[sp] = n; stk_depth[sp] = 2 * lg; sp++;
     while (sp) {
         --sp;
         int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        bool heapsorted = false;
         while (last - first > 16) {
             if (depth == 0) {  // heapsort fallback: never reached by real scenes, kept serial
                 if (lane == 0) sort_heapsort(A, first, last);
                 __syncwarp();
+                heapsorted = true;
                 break;
             }
             --depth;
@@ -228,12 +272,65 @@ __device__ void std_sort_desc(const CandArray& A, int n) {
             stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
             last = cut;
         }
+        if (!heapsorted && last - first > 1) {  // a range the quicksort leaves to the final insertion sort
+            if (lane == 0) blocks[nblk] = ((unsigned) first << 16) | (unsigned) last;
+            nblk++;
+        }
     }
-    // __final_insertion_sort: __insertion_sort on the first 16 (or all), then unguarded inserts; both
-    // are "move left past everything smaller", bounded below by index 0
-    for (int i = 1; i < n; ++i) warp_linear_insert(A, i, 0);
+    __syncwarp();
+    // __final_insertion_sort (__insertion_sort on the first 16, then __unguarded_insertion_sort): every
+    // element moves left past the elements it is greater than.  After the partitioning above the array is
+    // a sequence of ranges of <= 16 elements (or heap-sorted ones) with  left range >= pivot >= right range,
+    // so no element ever crosses into the range on its left (`val > y` is false for every y there) and the
+    // ranges can be insertion-sorted independently: one lane per range, same comparisons and moves per
+    // element as the sequential pass, hence the same permutation.
+    for (int b = lane; b < nblk; b += 32) {
+        const int first = (int) (blocks[b] >> 16), last = (int) (blocks[b] & 0xffffu);
+        for (int i = first + 1; i < last; ++i) {
+            const Cand val = A.get(i);
+            int j = i;
+            while (j > first && val.s > A.s[j - 1]) { A.set(j, A.get(j - 1)); --j; }
+            if (j != i) A.set(j, val);
+        }
+    }
+    __syncwarp();
 }
 
+#ifdef EKP_CONN_PROFILE  // tools/ only: per-phase time of the slowest block and summed over blocks (ns)
+__device__ unsigned long long g_conn_prof[16];
+__device__ __forceinline__ unsigned long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PROF_MARK(k) do { if (threadIdx.x == 0) { const unsigned long long _t = prof_now(); atomicAdd(&g_conn_prof[k], _t - prof_t); atomicMax(&g_conn_prof[8 + k], _t - prof_t); prof_t = _t; } } while (0)
+extern "C" int ekp_debug_conn_profile(unsigned long long* out16, int reset) {
+    cudaMemcpyFromSymbol(out16, g_conn_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_conn_prof, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define PROF_MARK(k) do { } while (0)
+#endif
+
+// Ordered compaction step shared by both passes: every thread of the block contributes `flag`; returns the
+// number of flagged threads before this one plus `base`, and advances `base` by the block's total (identical
+// in every thread).  Two block barriers.
+__device__ __forceinline__ int ordered_slot(bool flag, int* sWarpCnt, int& base) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) sWarpCnt[warp] = __popc(mask);
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < kConnThreads / 32; k++) {
+        const int c = sWarpCnt[k];
+        if (k < warp) before += c;
+        all += c;
+    }
+    const int pos = base + before + __popc(mask & ((1u << lane) - 1u));
+    base += all;
+    __syncthreads();
+    return pos;
+}
+
+template <bool kVec2>
 __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_peak* __restrict__ line,
                                                                    const int* __restrict__ part_off, int max_peaks,
                                                                    const PafSource paf, int h1, Conn* __restrict__ conns,
@@ -243,9 +340,11 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     __shared__ float sScore[EKP_MAX_CAND];
     __shared__ unsigned sTag[EKP_MAX_CAND];
     __shared__ float sScore2[EKP_MAX_CAND];
-    __shared__ unsigned sTag2[EKP_MAX_CAND];
+    __shared__ unsigned sTag2[EKP_MAX_CAND];   // pass-1 survivors while scoring, then the ranked tags
     __shared__ int sTies;
     __shared__ int sWarpCnt[kConnThreads / 32];
+    __shared__ unsigned sUsedA[EKP_MAX_PART / 32], sUsedB[EKP_MAX_PART / 32];
+    static_assert(kSurvWindow <= EKP_MAX_CAND, "the survivor list lives in sTag2");
     const int limb = blockIdx.x, img = blockIdx.y;
     const int pa = kPairs[limb][0], pb = kPairs[limb][1];
     const int ch1 = kPairsNet[limb][0], ch2 = kPairsNet[limb][1];
@@ -257,46 +356,62 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
         if (threadIdx.x == 0) *out_n = 0;
         return;
     }
+#ifdef EKP_CONN_PROFILE
+    unsigned long long prof_t = prof_now();
+#endif
     const ekp_peak* L = line + (size_t) img * max_peaks;
     for (int i = threadIdx.x; i < nA; i += kConnThreads) sA[i] = L[offA + i];
     for (int i = threadIdx.x; i < nB; i += kConnThreads) sB[i] = L[offB + i];
+    if (threadIdx.x < EKP_MAX_PART / 32) sUsedA[threadIdx.x] = sUsedB[threadIdx.x] = 0u;
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- stage 4: score all nA x nB pairs; candidates end up in pair order (a outer, b inner) --------
+    PROF_MARK(0);  // peaks staged
     const int npairs = nA * nB;
     int total = 0;  // candidates so far, identical in every thread
-    for (int base = 0; base < npairs; base += kConnThreads) {
-        const int pidx = base + threadIdx.x;
-        bool pass = false;
-        float crit = 0.f;
-        int ia = 0, ib = 0;
-        if (pidx < npairs) {
-            ia = pidx / nB;
-            ib = pidx - ia * nB;
-            pass = score_pair(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit);
+    // Few pairs (every scene but a crowd): one pass, one round trip to memory.  Otherwise pass 1 thins them out.
+    const bool two_pass = npairs > 2 * kConnThreads;
+    for (int win = 0; win < npairs; win += kSurvWindow) {
+        const int win_end = min(win + kSurvWindow, npairs);
+        int nsurv = 0;  // pass 1: pairs of this window that can still pass, in pair order
+        if (!two_pass) {
+            nsurv = win_end - win;
+            for (int k = threadIdx.x; k < nsurv; k += kConnThreads) sTag2[k] = (unsigned) (win + k);
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, pass);
-        if (lane == 0) sWarpCnt[warp] = __popc(mask);
+        for (int base = win; two_pass && base < win_end; base += kConnThreads) {
+            const int pidx = base + threadIdx.x;
+            bool keep = false;
+            if (pidx < win_end) {
+                const int ia = pidx / nB;
+                keep = pair_may_pass<kVec2>(sA[ia], sB[pidx - ia * nB], paf, img, ch1, ch2);
+            }
+            const int pos = ordered_slot(keep, sWarpCnt, nsurv);
+            if (keep) sTag2[pos] = (unsigned) pidx;
+        }
         __syncthreads();
-        int before = 0, all = 0;
-#pragma unroll
-        for (int k = 0; k < kConnThreads / 32; k++) {
-            const int c = sWarpCnt[k];
-            if (k < warp) before += c;
-            all += c;
+        PROF_MARK(1);  // pass 1
+        for (int base = 0; base < nsurv; base += kConnThreads) {  // pass 2: the full evaluation of the survivors
+            const int k = base + threadIdx.x;
+            bool pass = false;
+            float crit = 0.f;
+            int ia = 0, ib = 0;
+            if (k < nsurv) {
+                const int pidx = (int) sTag2[k];
+                ia = pidx / nB;
+                ib = pidx - ia * nB;
+                pass = score_pair<kVec2>(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit);
+            }
+            const int pos = ordered_slot(pass, sWarpCnt, total);
+            if (pass && pos < EKP_MAX_CAND) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
         }
-        if (pass) {
-            const int pos = total + before + __popc(mask & ((1u << lane) - 1u));
-            if (pos < EKP_MAX_CAND) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
-        }
-        total += all;
-        __syncthreads();
+        __syncthreads();  // the survivor list is rewritten by the next window
+        PROF_MARK(2);  // pass 2
     }
 
     // ---- sort (pafprocess.cpp:97).  std::sort's result is only algorithm-dependent in how it
     // permutes EQUAL scores, and for n <= 16 it is a plain (stable) insertion sort.  So: rank every
     // candidate in parallel (stable order) and detect ties; only when n > 16 AND ties exist does
-    // one thread replay libstdc++'s introsort on the original sequence.
+    // one warp replay libstdc++'s introsort on the original sequence.
     const int n = min(total, EKP_MAX_CAND);
     if (threadIdx.x == 0) {
         sTies = 0;
@@ -318,52 +433,74 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     }
     __syncthreads();
 
+    PROF_MARK(3);  // rank sort
+    if (threadIdx.x >= 32) return;
     const bool replay = n > 16 && sTies;  // uniform
-    if (replay && threadIdx.x < 32) {    // warp 0 replays libstdc++'s std::sort on the original sequence
+    if (replay) {                           // warp 0 replays libstdc++'s std::sort on the original sequence
         CandArray A;
         A.s = sScore; A.t = sTag;
-        std_sort_desc(A, n);
+        std_sort_desc(A, n, sTag2);  // the ranked copy is not needed when the replay decides the order
     }
-    if (threadIdx.x == 0) {
-        const float* srcS = replay ? sScore : sScore2;
-        const unsigned* srcT = replay ? sTag : sTag2;
-        // greedy assignment, pafprocess.cpp:98-124 (a peak is used at most once per limb side)
-        unsigned usedA[EKP_MAX_PART / 32], usedB[EKP_MAX_PART / 32];
-#pragma unroll
-        for (int k = 0; k < EKP_MAX_PART / 32; k++) usedA[k] = usedB[k] = 0u;
-        Conn* out = conns + ((size_t) img * EKP_NUM_LIMB + limb) * EKP_MAX_PART;
-        int nc = 0;
-        for (int c = 0; c < n; c++) {
-            const unsigned tag = srcT[c];
-            const int i1 = tag >> 16, i2 = tag & 0xffff;
-            if ((usedA[i1 >> 5] >> (i1 & 31)) & 1u) continue;
-            if ((usedB[i2 >> 5] >> (i2 & 31)) & 1u) continue;
-            usedA[i1 >> 5] |= 1u << (i1 & 31);
-            usedB[i2 >> 5] |= 1u << (i2 & 31);
-            Conn cn;
-            cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c]; cn.pad = 0;
-            out[nc++] = cn;
+    __syncwarp();
+    PROF_MARK(4);  // std::sort replay
+    // ---- greedy assignment, pafprocess.cpp:98-124: walk the sorted candidates, accept one iff neither of its
+    // peaks is used yet on this limb.  Warp 0 takes 32 candidates at a time: the lowest lane whose two peaks
+    // are still free is the next accepted connection (same order as the sequential walk); its peaks
+    // knock out the other lanes' candidates, and the used sets carry over to the next 32.
+    const float* srcS = replay ? sScore : sScore2;
+    const unsigned* srcT = replay ? sTag : sTag2;
+    const int lane = threadIdx.x;
+    Conn* out = conns + ((size_t) img * EKP_NUM_LIMB + limb) * EKP_MAX_PART;
+    int nc = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int c = c0 + lane;
+        const unsigned tag = c < n ? srcT[c] : 0u;
+        const int i1 = tag >> 16, i2 = tag & 0xffff;
+        bool alive = c < n && !((sUsedA[i1 >> 5] >> (i1 & 31)) & 1u) && !((sUsedB[i2 >> 5] >> (i2 & 31)) & 1u);
+        for (;;) {
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (!m) break;
+            const int leader = __ffs(m) - 1;
+            const int l1 = __shfl_sync(0xffffffffu, i1, leader), l2 = __shfl_sync(0xffffffffu, i2, leader);
+            if (lane == leader) {
+                Conn cn;
+                cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c]; cn.pad = 0;
+                out[nc] = cn;
+                sUsedA[i1 >> 5] |= 1u << (i1 & 31);
+                sUsedB[i2 >> 5] |= 1u << (i2 & 31);
+            }
+            if (i1 == l1 || i2 == l2) alive = false;
+            nc++;
         }
-        *out_n = nc;
+        __syncwarp();  // the used sets are read by every lane at the top of the next chunk
     }
+    if (lane == 0) *out_n = nc;
+    PROF_MARK(5);  // greedy
+#ifdef EKP_CONN_PROFILE
+    if (threadIdx.x == 0) { atomicAdd(&g_conn_prof[6], (unsigned long long) n); atomicMax(&g_conn_prof[14], (unsigned long long) n); atomicAdd(&g_conn_prof[7], (unsigned long long) replay); }
+#endif
 }
 
 // Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one warp), so that the tie permutation -- including the heapsort fallback, which real scenes never
 // reach -- can be compared with the compiled reference's std::sort.
-__global__ void debug_std_sort_kernel(float* scores, unsigned* tags, int n) {
+__global__ void debug_std_sort_kernel(float* scores, unsigned* tags, int n, unsigned* scratch) {
     CandArray A;  // one warp, as in paf_connect_kernel
     A.s = scores; A.t = tags;
-    std_sort_desc(A, n);
+    std_sort_desc(A, n, scratch);
 }
-cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, cudaStream_t stream) {
-    debug_std_sort_kernel<<<1, 32, 0, stream>>>(scores, tags, n);
+cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned* scratch, cudaStream_t stream) {
+    debug_std_sort_kernel<<<1, 32, 0, stream>>>(scores, tags, n, scratch);
     return cudaGetLastError();
 }
 
 cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int max_peaks, const PafSource& paf, int h1,
                                int n, Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream) {
     dim3 grid(EKP_NUM_LIMB, n);
-    paf_connect_kernel<<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);
+    // both PAF channels of a limb with one 8-byte load: channel-last tensor, even channel count, aligned base
+    const bool channel_last = paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC;
+    const bool vec2 = channel_last && paf.C % 2 == 0 && reinterpret_cast<uintptr_t>(paf.ptr) % 8 == 0;
+    if (vec2) paf_connect_kernel<true><<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);
+    else paf_connect_kernel<false><<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);
     return cudaGetLastError();
 }
 
