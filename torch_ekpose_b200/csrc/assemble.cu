@@ -2,33 +2,24 @@
 // warp per image.  Replaces /root/reference/lib/pafprocess/pafprocess.cpp:127-191 (subset
 // assembly and pruning) and the getter loop of paf_to_pose_cpp (paf_to_pose.py:361-377).
 //
-// The assembly is inherently sequential over (limb, connection) and is kept so; only the row
-// SEARCH (pafprocess.cpp:137-144) and the 18-column merge (:160-161) are spread over the warp's
-// lanes, which cannot change the result.  Quirks that are part of the observable behaviour are
-// reproduced: rows hold cids as floats, the merge test is `> 0` (cid 0 counts as absent), a
-// connection matching three or more rows is dropped, limb 18 never starts a person, and peak
-// scores are looked up by cid in the part-sorted table.
+// The reference walks (limb, connection) strictly in order (pafprocess.cpp:130-185).  Within ONE limb,
+// however, the connections carry distinct cid1 and distinct cid2 (the greedy step uses every peak at most
+// once per limb side), so they can only interact through a subset row that two of them match, or through
+// a merge.  Per limb, one lane per connection searches the rows as they stand at the start of the limb
+// (pafprocess.cpp:137-144); if every connection matches at most one row and no row is matched twice, all
+// of them are applied at once -- extend (:146-151) or start a row (:173-183, new rows numbered in
+// connection order) -- which is exactly what the sequential walk produces (argument at limb_parallel).
+// Otherwise (a merge, a shared row: rare) the limb is walked sequentially, rows searched by the lanes.
+// Quirks that are part of the observable behaviour are reproduced: rows hold cids as floats, the merge
+// test is `> 0` (cid 0 counts as absent), a connection matching three or more rows is dropped, limb 18
+// never starts a person, and peak scores are looked up by cid in the part-sorted table.
 //
-// A single warp running dependent code pays full latency on every instruction, so:
-//  * the image's connections and peak scores are staged in shared memory first (coalesced);
-//  * up to 64 candidate people live in REGISTERS, two subset rows per lane (the 19-limb loop is
-//    unrolled so every column index is a compile-time constant); extending or starting a row costs
-//    one broadcast load, two compares and two ballots.  Merges and a 65th row continue, from the
-//    same connection, on the general shared-memory path below (same arithmetic, any row count);
-//  * results go to one packed record per image (ResultLayout): one device-to-host copy per batch.
+// One warp per image; the image's connections and peak scores are staged in shared memory first
+// (coalesced, one flat pass); results go to one packed record per image (ResultLayout): one
+// device-to-host copy per batch.
 #include "common.cuh"
 
 namespace ekp {
-
-// pafprocess.h:21-24 as compile-time constants for the unrolled fast path
-__host__ __device__ constexpr int limb_a(int l) {
-    constexpr int t[EKP_NUM_LIMB] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
-    return t[l];
-}
-__host__ __device__ constexpr int limb_b(int l) {
-    constexpr int t[EKP_NUM_LIMB] = {2, 5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 0, 14, 16, 15, 17, 16, 17};
-    return t[l];
-}
 
 // Everything the sequential loop needs about one connection, prepared in parallel while staging:
 // the cids as floats (rows hold floats) and the two score sums the reference forms
@@ -41,114 +32,154 @@ struct __align__(16) ConnRec {
     float pad0, pad1, pad2;
 };
 
-__device__ __forceinline__ ConnRec make_rec(const Conn& cn, const ekp_peak* L) {
+__device__ __forceinline__ ConnRec make_rec(const Conn& cn) {
     ConnRec r;
     r.f1 = (float) cn.cid1;
     r.f2 = (float) cn.cid2;
     r.score = cn.score;
-    const float p1 = L[cn.cid1].score, p2 = L[cn.cid2].score;
-    r.s_ext = __fadd_rn(p2, cn.score);
-    r.s_new = __fadd_rn(__fadd_rn(p1, p2), cn.score);
+    r.s_ext = cn.s_ext;  // formed by paf_connect_kernel
+    r.s_new = cn.s_new;
     r.pad0 = r.pad1 = r.pad2 = 0.f;
     return r;
 }
 
 struct AsmInput {
-    const ConnRec* sRec;  // staged records (or nullptr -> build from `conns` / `L` on the fly)
+    const ConnRec* sRec;  // staged records (or nullptr -> build from `conns` on the fly)
     const int* sStart;    // [20] prefix of per-limb counts
     const Conn* conns;    // this image's [19][EKP_MAX_PART]
-    const ekp_peak* L;    // this image's part-sorted peak table
     __device__ __forceinline__ ConnRec rec_at(int limb, int k) const {
-        return sRec ? sRec[sStart[limb] + k] : make_rec(conns[(size_t) limb * EKP_MAX_PART + k], L);
+        return sRec ? sRec[sStart[limb] + k] : make_rec(conns[(size_t) limb * EKP_MAX_PART + k]);
     }
 };
 
-// ---- fast path: R subset rows per lane, in registers ------------------------------------------
-// Row index i lives in lane (i & 31), slot (i >> 5); capacity 32*R rows.  It handles the two cases
-// that make up almost every step -- a connection extends one row (found == 1) or starts a new one
-// (found == 0) -- with one broadcast load, R compares and R ballots.  When a connection matches
-// TWO rows (a merge, rare) or a row beyond the capacity is needed, the rows are written to shared
-// memory and the caller continues from exactly that connection on the general path.  The 19-limb
-// loop is unrolled (column indices must be compile-time for registers), so the per-limb body is
-// kept this small on purpose: the whole path has to stay inside the instruction cache.
-template <int R>
-__device__ void assemble_in_registers(const AsmInput& in, int max_humans, float* __restrict__ rows_out, int& nrows_out,
-                                      int& resume_limb, int& resume_k) {
+// ---- one limb, all connections at once -------------------------------------------------------------
+// Let the limb's connections be k = 0..nc-1 (acceptance order), with distinct f1 (cid1) and distinct f2
+// (cid2).  Against the rows at the START of the limb, connection k matches found_k rows.  Claim: if every
+// found_k <= 1 and the matched rows are pairwise different, the sequential walk takes, for every k, the same
+// branch on the same row as it would at the start of the limb:
+//  * an earlier j that EXTENDS its row R_j only changes R_j[p2] (to f2_j != f2_k), R_j[18], R_j[19]; k did
+//    not match R_j, and cannot start to (R_j[p1] is unchanged, R_j[p2] becomes f2_j != f2_k);
+//  * an earlier j that STARTS a row gives it p1 = f1_j != f1_k and p2 = f2_j != f2_k: no match for k;
+//  * a j whose single match is through p2 only changes nothing (pafprocess.cpp:147).
+// So extensions touch pairwise different rows, new rows are appended in connection order, and the result
+// equals the sequential one.  Returns false (state untouched) when the condition does not hold.
+__device__ bool limb_parallel(const AsmInput& in, int limb, int max_humans, float* __restrict__ rows, int& nrows_io, bool& ovf,
+                              int* __restrict__ sClaim /* [max_humans] */, short* __restrict__ sMatch /* [EKP_MAX_PART] */) {
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
-    float r[R][20];
-#pragma unroll
-    for (int s = 0; s < R; s++)
-#pragma unroll
-        for (int q = 0; q < 20; q++) r[s][q] = -1.0f;
-    int nrows = 0;
-    const int cap = max_humans < 32 * R ? max_humans : 32 * R;
-    resume_limb = EKP_NUM_LIMB;  // "finished"
-    resume_k = 0;
-    bool bail = false;
-#pragma unroll
-    for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
-        const int p1 = limb_a(limb), p2 = limb_b(limb);
-        const int nc = in.sStart[limb + 1] - in.sStart[limb];
-        for (int k = 0; k < nc; k++) {
-            const ConnRec cn = in.rec_at(limb, k);
-            int found = 0;
-            bool m[R];
-#pragma unroll
-            for (int s = 0; s < R; s++) {  // row search, pafprocess.cpp:137-144
-                m[s] = (32 * s + lane) < nrows && (r[s][p1] == cn.f1 || r[s][p2] == cn.f2);
-                found += __popc(__ballot_sync(FULL, m[s]));
+    const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
+    const int nc = in.sStart[limb + 1] - in.sStart[limb];
+    const int nrows = nrows_io;
+    if (nc <= 32) {  // the usual case: one connection per lane, everything in registers
+        const bool active = lane < nc;
+        ConnRec cn;
+        int found = 0, s1 = -1;
+        if (active) {
+            cn = in.rec_at(limb, lane);
+            for (int r = 0; r < nrows; r++) {  // every lane reads the same two words: broadcast
+                const bool m = rows[r * 20 + p1] == cn.f1 || rows[r * 20 + p2] == cn.f2;
+                if (m) { found++; s1 = r; }
             }
-            if (found == 1) {
-#pragma unroll
-                for (int s = 0; s < R; s++)
-                    if (m[s] && r[s][p2] != cn.f2) {
-                        r[s][p2] = cn.f2;
-                        r[s][19] = __fadd_rn(r[s][19], 1.0f);
-                        r[s][18] = __fadd_rn(r[s][18], cn.s_ext);
-                    }
-            } else if (found == 0) {
-                if (limb < 18) {
-                    if (nrows >= cap) { bail = true; resume_limb = limb; resume_k = k; break; }
-#pragma unroll
-                    for (int s = 0; s < R; s++)
-                        if (32 * s + lane == nrows) {
-#pragma unroll
-                            for (int q = 0; q < 18; q++) r[s][q] = -1.0f;
-                            r[s][p1] = cn.f1;
-                            r[s][p2] = cn.f2;
-                            r[s][19] = 2.0f;
-                            r[s][18] = cn.s_new;
-                        }
-                    nrows++;
-                }
-            } else if (found == 2) {  // merge or extend-with-conflict: continue on the general path
-                bail = true; resume_limb = limb; resume_k = k;
-                break;
-            }  // found >= 3: the reference takes no branch
         }
-        if (bail) break;
+        // a row matched by two connections shows up as two lanes with the same s1
+        const unsigned peers = __match_any_sync(FULL, s1 >= 0 ? s1 : -1 - lane);
+        if (__any_sync(FULL, found >= 2 || (s1 >= 0 && (peers & (peers - 1)) != 0u))) return false;
+        if (s1 >= 0) {  // found == 1, pafprocess.cpp:146-151
+            if (rows[s1 * 20 + p2] != cn.f2) {
+                rows[s1 * 20 + p2] = cn.f2;
+                rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
+                rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
+            }
+        }
+        const bool starts = active && s1 < 0 && limb < 18;  // found == 0, :173-183
+        const unsigned mask = __ballot_sync(FULL, starts);
+        if (starts) {
+            const int r = nrows + __popc(mask & ((1u << lane) - 1u));
+            if (r < max_humans) {
+#pragma unroll
+                for (int q = 0; q < 18; q++) rows[r * 20 + q] = -1.0f;
+                rows[r * 20 + p1] = cn.f1;
+                rows[r * 20 + p2] = cn.f2;
+                rows[r * 20 + 18] = cn.s_new;
+                rows[r * 20 + 19] = 2.0f;
+            }
+        }
+        int nnew = __popc(mask);
+        if (nrows + nnew > max_humans) { ovf = true; nnew = max_humans - nrows; }
+        nrows_io = nrows + nnew;
+        __syncwarp();
+        return true;
     }
-#pragma unroll
-    for (int s = 0; s < R; s++)
-        if (32 * s + lane < nrows) {
-#pragma unroll
-            for (int q = 0; q < 20; q++) rows_out[(32 * s + lane) * 20 + q] = r[s][q];
+    // search: matched row (or -1: none) per connection; two or more matches end the attempt
+    bool bad = false;
+    for (int k0 = 0; k0 < nc; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < nc) {
+            const ConnRec cn = in.rec_at(limb, k);
+            int found = 0, s1 = -1;
+            for (int r = 0; r < nrows; r++) {  // every lane reads the same two words: broadcast
+                const bool m = rows[r * 20 + p1] == cn.f1 || rows[r * 20 + p2] == cn.f2;
+                if (m) { found++; s1 = r; }
+            }
+            if (found >= 2) bad = true;
+            sMatch[k] = (short) s1;
         }
-    nrows_out = nrows;
+    }
+    if (__any_sync(FULL, bad)) return false;
     __syncwarp();
+    for (int k = lane; k < nc; k += 32)  // no row may be matched by two connections
+        if (sMatch[k] >= 0) sClaim[sMatch[k]] = k;
+    __syncwarp();
+    for (int k = lane; k < nc; k += 32)
+        if (sMatch[k] >= 0 && sClaim[sMatch[k]] != k) bad = true;
+    if (__any_sync(FULL, bad)) return false;
+    // apply
+    int nnew = 0;  // rows started so far by this limb (identical in every lane)
+    for (int k0 = 0; k0 < nc; k0 += 32) {
+        const int k = k0 + lane;
+        bool starts = false;
+        ConnRec cn;
+        if (k < nc) {
+            cn = in.rec_at(limb, k);
+            const int s1 = sMatch[k];
+            if (s1 >= 0) {  // found == 1, pafprocess.cpp:146-151
+                if (rows[s1 * 20 + p2] != cn.f2) {
+                    rows[s1 * 20 + p2] = cn.f2;
+                    rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
+                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
+                }
+            } else {
+                starts = limb < 18;  // found == 0, :173-183
+            }
+        }
+        const unsigned mask = __ballot_sync(FULL, starts);
+        if (starts) {
+            const int r = nrows + nnew + __popc(mask & ((1u << lane) - 1u));
+            if (r < max_humans) {
+#pragma unroll
+                for (int q = 0; q < 18; q++) rows[r * 20 + q] = -1.0f;
+                rows[r * 20 + p1] = cn.f1;
+                rows[r * 20 + p2] = cn.f2;
+                rows[r * 20 + 18] = cn.s_new;
+                rows[r * 20 + 19] = 2.0f;
+            }
+        }
+        nnew += __popc(mask);
+    }
+    if (nrows + nnew > max_humans) { ovf = true; nnew = max_humans - nrows; }
+    nrows_io = nrows + nnew;
+    __syncwarp();
+    return true;
 }
 
-// ---- general path: rows in shared memory, any count up to max_humans ---------------------------
-// Starts at connection k0 of limb limb0 with nrows_io rows already in `rows`.
-__device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __restrict__ rows, int& nrows_io, bool& ovf,
-                                 int limb0, int k0) {
+// ---- one limb, connection by connection (the reference's walk; the row search is spread over the lanes) ----
+__device__ void limb_sequential(const AsmInput& in, int limb, int max_humans, float* __restrict__ rows, int& nrows_io, bool& ovf) {
     const int lane = threadIdx.x;
     int nrows = nrows_io;
-    for (int limb = limb0; limb < EKP_NUM_LIMB; limb++) {
+    {
         const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
         const int nc = in.sStart[limb + 1] - in.sStart[limb];
-        for (int k = (limb == limb0 ? k0 : 0); k < nc; k++) {
+        for (int k = 0; k < nc; k++) {
             const ConnRec cn = in.rec_at(limb, k);
             const float f1 = cn.f1, f2 = cn.f2;
             int found = 0, s1 = 0, s2 = 0;
@@ -214,6 +245,21 @@ __device__ void assemble_in_smem(const AsmInput& in, int max_humans, float* __re
     nrows_io = nrows;
 }
 
+#ifdef EKP_ASM_PROFILE  // tools/ only: time per phase summed over images (ns) and limb counts
+__device__ unsigned long long g_asm_prof[8];
+__device__ __forceinline__ unsigned long long asm_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define APROF(k) do { if (threadIdx.x == 0) { const unsigned long long _t = asm_now(); atomicAdd(&g_asm_prof[k], _t - prof_t); prof_t = _t; } } while (0)
+#define ACOUNT(k) do { if (threadIdx.x == 0) atomicAdd(&g_asm_prof[k], 1ull); } while (0)
+extern "C" int ekp_debug_asm_profile(unsigned long long* out8, int reset) {
+    cudaMemcpyFromSymbol(out8, g_asm_prof, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_asm_prof, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define APROF(k) do { } while (0)
+#define ACOUNT(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict__ line, int max_peaks,
                                                       const int* __restrict__ n_peaks, const Conn* __restrict__ conns,
                                                       const int* __restrict__ n_conns, int max_humans, int conn_cap,
@@ -224,8 +270,12 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     ConnRec* sRec = reinterpret_cast<ConnRec*>(rows + (size_t) (max_humans < 32 ? 32 : max_humans) * 20);  // [conn_cap]
     int* sKept = reinterpret_cast<int*>(sRec + conn_cap);                                         // [max_humans]
     __shared__ int sStart[EKP_NUM_LIMB + 1];
+    __shared__ short sMatch[EKP_MAX_PART];  // limb_parallel: matched row per connection
 
     const int img = blockIdx.x, lane = threadIdx.x;
+#ifdef EKP_ASM_PROFILE
+    unsigned long long prof_t = asm_now();
+#endif
     const ekp_peak* L = line + (size_t) img * max_peaks;
     const Conn* Cimg = conns + (size_t) img * EKP_NUM_LIMB * EKP_MAX_PART;
     const int npk = n_peaks[img];
@@ -251,7 +301,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
             int limb = 0;
 #pragma unroll
             for (int l = 1; l < EKP_NUM_LIMB; l++) limb += (idx >= sStart[l]);
-            sRec[idx] = make_rec(Cimg[(size_t) limb * EKP_MAX_PART + (idx - sStart[limb])], L);
+            sRec[idx] = make_rec(Cimg[(size_t) limb * EKP_MAX_PART + (idx - sStart[limb])]);
         }
     }
     __syncwarp();
@@ -259,17 +309,20 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     in.sRec = staged ? sRec : nullptr;
     in.sStart = sStart;
     in.conns = Cimg;
-    in.L = L;
 
-    // ---- sequential assembly ------------------------------------------------------------------
+    APROF(0);  // staging
+    // ---- assembly, limb by limb (pafprocess.cpp:130-185) ------------------------------------------
     int nrows = 0;
     bool ovf = false;
-    // Registers hold up to 64 rows (two per lane); whatever they cannot do (merges, more rows) continues
-    // on the shared-memory path from the connection where they stopped.
-    int resume_limb = 0, resume_k = 0;
-    if (max_humans >= 1) assemble_in_registers<2>(in, max_humans, rows, nrows, resume_limb, resume_k);
-    if (resume_limb < EKP_NUM_LIMB) assemble_in_smem(in, max_humans, rows, nrows, ovf, resume_limb, resume_k);
-    __syncwarp();
+    for (int limb = 0; limb < EKP_NUM_LIMB; limb++) {
+        if (sStart[limb + 1] == sStart[limb]) continue;
+        if (!limb_parallel(in, limb, max_humans, rows, nrows, ovf, sKept /* free until the prune */, sMatch)) {
+            APROF(1);
+            limb_sequential(in, limb, max_humans, rows, nrows, ovf);
+            APROF(2); ACOUNT(5);
+        } else { APROF(1); ACOUNT(4); }
+        __syncwarp();
+    }
 
     // ---- prune (pafprocess.cpp:187-191: a reverse erase loop == an order-preserving filter) and
     //      write the image's result record, all lanes busy --------------------------------------
@@ -306,6 +359,7 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
         const int r = sKept[k];
         hs[k] = __fdiv_rn(rows[r * 20 + 18], rows[r * 20 + 19]);  // get_score
     }
+    APROF(3);  // prune + record
     if (lane == 0) {
         int4 head;
         head.x = kept;

@@ -19,10 +19,13 @@ struct RawPeak {
     unsigned key;   // order within the part: (row << 16 | col) of the maximum, or the input index
 };
 
-struct Conn {        // pafprocess.h:45-51
+struct __align__(16) Conn {  // pafprocess.h:45-51, plus the two score sums the assembly forms from it
     int cid1, cid2;
     float score;
-    int pad;
+    float s_ext;   // peak_score(cid2) + score                      (pafprocess.cpp:150/171: a row is extended by part2)
+    float s_new;   // (peak_score(cid1) + peak_score(cid2)) + score (:179-181: a new row), peak scores looked up by
+                   // cid in the part-sorted table like the reference's peak_infos_line[cid]
+    int pad0, pad1, pad2;
 };
 
 // how stage 4 obtains paf_mat[y][x][ch]

@@ -464,7 +464,8 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
             const int l1 = __shfl_sync(0xffffffffu, i1, leader), l2 = __shfl_sync(0xffffffffu, i2, leader);
             if (lane == leader) {
                 Conn cn;
-                cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c]; cn.pad = 0;
+                cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c];
+                cn.s_ext = cn.s_new = 0.f; cn.pad0 = cn.pad1 = cn.pad2 = 0;
                 out[nc] = cn;
                 sUsedA[i1 >> 5] |= 1u << (i1 & 31);
                 sUsedB[i2 >> 5] |= 1u << (i2 & 31);
@@ -475,6 +476,15 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
         __syncwarp();  // the used sets are read by every lane at the top of the next chunk
     }
     if (lane == 0) *out_n = nc;
+    // the score sums the assembly needs per connection, here where 19 x n warps can fetch the peak scores in
+    // parallel (one warp per image would pay the two dependent round trips alone)
+    __syncwarp();
+    for (int k = lane; k < min(nc, EKP_MAX_PART); k += 32) {
+        const float sc = out[k].score;
+        const float p1 = L[out[k].cid1].score, p2 = L[out[k].cid2].score;
+        out[k].s_ext = __fadd_rn(p2, sc);
+        out[k].s_new = __fadd_rn(__fadd_rn(p1, p2), sc);
+    }
     PROF_MARK(5);  // greedy
 #ifdef EKP_CONN_PROFILE
     if (threadIdx.x == 0) { atomicAdd(&g_conn_prof[6], (unsigned long long) n); atomicMax(&g_conn_prof[14], (unsigned long long) n); atomicAdd(&g_conn_prof[7], (unsigned long long) replay); }

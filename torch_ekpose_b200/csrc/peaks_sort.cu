@@ -38,22 +38,28 @@ __global__ void peaks_ingest_kernel(const float* __restrict__ peaks, const int* 
     raw[(size_t) img * raw_cap + k] = pk;
 }
 
-// One block per image.  Dynamic shared memory: raw_cap 64-bit keys.
-__global__ void __launch_bounds__(256) peaks_sort_kernel(const RawPeak* __restrict__ raw, const int* __restrict__ raw_count,
-                                                         int raw_cap, int id_from_key, ekp_peak* __restrict__ line,
-                                                         int* __restrict__ part_off /* [n][20] */, int* __restrict__ n_peaks,
-                                                         unsigned* __restrict__ overflow) {
+// Blocks (slice, image): every block stages all of the image's keys in shared memory (dynamic: raw_cap
+// 64-bit keys), ranks the 256 peaks of its slice against them (the inner loop reads one key per
+// step, broadcast to all threads) and scatters them to their rows; slice 0 also builds the per-part
+// offsets.  Crowded images (hundreds of peaks) thus spread over several SMs instead of one.
+constexpr int kSortThreads = 256;
+__global__ void __launch_bounds__(kSortThreads) peaks_sort_kernel(const RawPeak* __restrict__ raw, const int* __restrict__ raw_count,
+                                                                  int raw_cap, int id_from_key, ekp_peak* __restrict__ line,
+                                                                  int* __restrict__ part_off /* [n][20] */,
+                                                                  int* __restrict__ n_peaks, unsigned* __restrict__ overflow) {
     extern __shared__ unsigned long long sKey[];
     __shared__ int sCount[EKP_NUM_PART + 1];
-    const int img = blockIdx.x;
+    const int img = blockIdx.y, slice = blockIdx.x;
     const int total = raw_count[img];
     const int n = min(total, raw_cap);
+    if (slice * kSortThreads >= n && slice > 0) return;  // nothing in this slice (slice 0 always writes the offsets)
     const RawPeak* r = raw + (size_t) img * raw_cap;
     if (threadIdx.x <= EKP_NUM_PART) sCount[threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = threadIdx.x; i < n; i += kSortThreads)
         sKey[i] = ((unsigned long long) (unsigned) r[i].part << 32) | r[i].key;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int i = slice * kSortThreads + threadIdx.x;
+    if (i < n) {
         const unsigned long long k = sKey[i];
         int rank = 0;
         for (int j = 0; j < n; j++) {
@@ -65,8 +71,9 @@ __global__ void __launch_bounds__(256) peaks_sort_kernel(const RawPeak* __restri
         out.x = pk.x; out.y = pk.y; out.score = pk.score;
         out.id = id_from_key ? (int) pk.key : rank;
         line[(size_t) img * raw_cap + rank] = out;
-        atomicAdd(&sCount[min(pk.part, EKP_NUM_PART)], 1);
     }
+    if (slice != 0) return;
+    for (int j = threadIdx.x; j < n; j += kSortThreads) atomicAdd(&sCount[min((int) (sKey[j] >> 32), EKP_NUM_PART)], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned ovf = 0;
@@ -102,7 +109,8 @@ cudaError_t configure_peaks_sort(int raw_cap) {
 cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int id_from_key, int n, ekp_peak* line,
                               int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream) {
     const size_t smem = sizeof(unsigned long long) * (size_t) raw_cap;
-    peaks_sort_kernel<<<n, 256, smem, stream>>>(raw, raw_count, raw_cap, id_from_key, line, part_off, n_peaks, overflow);
+    dim3 grid((raw_cap + kSortThreads - 1) / kSortThreads, n);
+    peaks_sort_kernel<<<grid, kSortThreads, smem, stream>>>(raw, raw_count, raw_cap, id_from_key, line, part_off, n_peaks, overflow);
     return cudaGetLastError();
 }
 
