@@ -315,6 +315,60 @@ def test_run_peaks_random_lists_vs_oracle(pp):
         assert np.array_equal(got["x"], line[0]) and np.array_equal(got["id"], line[3])
 
 
+def _fuzz_scene(rng, H, W, people, drop, block, levels, per_part_cap=250):
+    """People on a jittered grid with randomly missing parts over a PAF field that is piecewise constant on
+    block x block cells with few distinct values: many pairs pass, many scores tie exactly, rows start
+    at different limbs and have to be merged, connections reach across people."""
+    tmpl = np.array([(0, -20), (0, -12), (-8, -12), (-12, -4), (-14, 4), (8, -12), (12, -4), (14, 4), (-5, 4), (-6, 14),
+                     (-6, 24), (5, 4), (6, 14), (6, 24), (-2, -22), (2, -22), (-4, -21), (4, -21)], np.float32)
+    rows, per_part = [], np.zeros(18, int)
+    for _ in range(people):
+        cx, cy = rng.integers(16, W - 16), rng.integers(26, H - 28)
+        sc = rng.uniform(0.6, 1.2)
+        for part in range(18):
+            if rng.random() < drop or per_part[part] >= per_part_cap:
+                continue
+            x = int(np.clip(cx + sc * tmpl[part, 0] + rng.integers(-1, 2), 0, W - 1))
+            y = int(np.clip(cy + sc * tmpl[part, 1] + rng.integers(-1, 2), 0, H - 1))
+            rows.append((x, y, rng.choice([0.25, 0.5, 0.75, 1.0]), 0, part))
+            per_part[part] += 1
+    peaks = np.array(rows, np.float32).reshape(-1, 5)
+    peaks = peaks[rng.permutation(len(peaks))]
+    hb, wb = (H + block - 1) // block, (W + block - 1) // block
+    coarse = rng.choice(levels, size=(hb, wb, 38)).astype(np.float32)
+    paf = np.repeat(np.repeat(coarse, block, axis=0), block, axis=1)[:H, :W].copy()
+    return peaks, paf
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_stage45_adversarial_fuzz_vs_oracle(ek, seed):
+    """Stages 4-5 on scenes built to hit every branch of the assembly and the sort: > 32 connections per
+    limb, connections that match two or three rows, merges, exact score ties among > 16 candidates (the
+    std::sort replay), unsorted input.  subset rows must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    H, W = 128, 192
+    cases = []
+    for people, drop, block, levels in [(4, 0.0, 8, [0.0, 1.0]), (12, 0.3, 16, [-1.0, 0.0, 0.5, 1.0]), (40, 0.15, 8, [0.0, 0.25, 1.0]),
+                                        (60, 0.5, 32, [0.5, 1.0]), (90, 0.2, 4, [-0.5, 0.0, 0.5, 1.0]), (25, 0.6, 64, [1.0])]:
+        cases.append(_fuzz_scene(rng, H, W, people, drop, block, levels))
+    n = len(cases)
+    stride = max(len(c[0]) for c in cases)
+    peaks = np.zeros((n, stride, 5), np.float32)
+    counts = np.array([len(c[0]) for c in cases], np.int32)
+    for i, c in enumerate(cases):
+        peaks[i, :counts[i]] = c[0]
+    paf = np.stack([c[1] for c in cases])
+    big = ek.PostProcessor(device=0, max_batch=n, max_h=16, max_w=24, max_peaks=2048, max_humans=512)
+    big.run_peaks(_dev(peaks), _dev(counts), _dev(paf), h1=H)
+    res = big.results()
+    for i in range(n):
+        sub, _ = util.oracle_people(peaks[i, :counts[i]], H, W, paf[i])
+        m = int(res["num_humans"][i])
+        assert m == len(sub), f"case {i}: {m} people vs {len(sub)}"
+        assert_bits_equal(res["subset"][i, :m], sub, f"case {i}")
+    big.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # capacity and argument errors are reported, never silent
 # ---------------------------------------------------------------------------------------------
