@@ -71,10 +71,15 @@ constexpr int kMatBlocks = EKP_MAT_BLOCKS;
 constexpr int kFillWarps = EKP_FILL_WARPS;      // warps that fill the store buffers and drive the TMA engine
 constexpr int kFillThreads = 32 * kFillWarps;
 constexpr int kNmsThreads = kMatThreads - kFillThreads;  // the other warps: heat patch, early-out, smoothing + NMS
-constexpr int kStoreBufs = EKP_STORE_BUFS;      // store buffers of [8 rows][kChunkCols float4] per CTA
+constexpr int kStoreBufs = EKP_STORE_BUFS;      // store buffers of [kChunkRows][kChunkCols float4] per CTA
 constexpr int kChunkCols = EKP_CHUNK_COLS;      // float4 columns per store chunk: one bulk copy = kChunkCols * 16 B of a row
 constexpr int kColsPerFillThread = kChunkCols / kFillThreads;
-constexpr int kStoreBufF4 = 8 * kChunkCols;
+#ifndef EKP_CHUNK_ROWS
+#define EKP_CHUNK_ROWS 8
+#endif
+constexpr int kChunkRows = EKP_CHUNK_ROWS;      // output rows per store chunk (8 = a whole stride-8 row pair, or 4)
+constexpr int kStoreBufF4 = kChunkRows * kChunkCols;
+static_assert(kChunkRows == 8 || kChunkRows == 4, "a chunk is a whole or half row pair");
 static_assert(kFillWarps >= 1 && kNmsThreads >= 32 && kNmsThreads % 32 == 0 && kChunkCols % kFillThreads == 0, "warp roles");
 enum { BAR_FILL = 1, BAR_NMS = 2, BAR_HEAT_READY = 3 };  // named barriers (0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -206,7 +211,7 @@ __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, i
                 }
         };
         float4* dst = reinterpret_cast<float4*>(out_img + ((size_t) Ystart * W + X0) * C) + c0;
-        auto emit = [&](auto k0_tag, auto n_tag) {  // rows k0 .. k0+n-1 of the current stride-8 row pair
+        auto emit_chunk = [&](auto k0_tag, auto n_tag) {  // rows k0 .. k0+n-1 of the current stride-8 row pair
             constexpr int K0 = decltype(k0_tag)::value, NN = decltype(n_tag)::value;
             float4* buf = sStore + (size_t) (phase % kStoreBufs) * kStoreBufF4;
             if (lane == 0) bulk_wait_read<kStoreBufs - 1>();  // the copies that last read this buffer are done reading
@@ -233,6 +238,15 @@ __device__ __forceinline__ void materialise_tile(const float* __restrict__ sP, i
             }
             dst += (size_t) NN * stride4;
             phase++;
+        };
+        auto emit = [&](auto k0_tag, auto n_tag) {  // ... in chunks of kChunkRows rows
+            constexpr int K0 = decltype(k0_tag)::value, NN = decltype(n_tag)::value;
+            if constexpr (NN > kChunkRows) {
+                emit_chunk(std::integral_constant<int, K0>{}, std::integral_constant<int, kChunkRows>{});
+                emit_chunk(std::integral_constant<int, K0 + kChunkRows>{}, std::integral_constant<int, NN - kChunkRows>{});
+            } else {
+                emit_chunk(k0_tag, n_tag);
+            }
         };
 #pragma unroll
         for (int s = 0; s < S; s++)
@@ -330,7 +344,7 @@ __device__ __forceinline__ TileGeom tile_geom(const DenseParams& p, int tile_x, 
 struct TileSmem {
     float* heat;    // [kHeatRows][tile_wl + 6][19]
     float* paf;     // [kPafRows][tile_wl + 2][38]
-    float4* store;  // [kStoreBufs][8][kChunkCols] float4 (materialising kernel only)
+    float4* store;  // [kStoreBufs][kChunkRows][kChunkCols] float4 (materialising kernel only)
 };
 
 // Everything a tile's threads share besides the patches.
