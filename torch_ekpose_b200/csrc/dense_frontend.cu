@@ -646,9 +646,9 @@ cudaError_t configure_dense_frontend() {
     return e;
 }
 
-// One CTA per tile.  (With per-thread stores, a persistent variant -- resident CTAs pulling tiles from a
-// counter with the next tile's patches prefetched into a double buffer -- was measured 7 % SLOWER on
-// B200, 0.442 vs 0.412 ms; see profiles/README.md.)
+// One CTA per tile.  (Persistent variants -- resident CTAs pulling tiles from a counter with the next tile's
+// patches prefetched into a second buffer -- were measured SLOWER on B200 twice: 0.442 vs 0.412 ms with
+// per-thread stores, 0.408 vs 0.381 ms with the bulk stores and warp roles; see profiles/README.md.)
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
     const size_t smem = dense_frontend_smem_bytes(p.tile_wl, p.paf_mat != nullptr && !p.smooth_out);
     dim3 grid((p.w + p.tile_wl - 1) / p.tile_wl, (p.h + kTB - 1) / kTB, p.n);
