@@ -66,9 +66,12 @@ def test_process_paf_known_answers(ek, case):
         assert n == 1 and float(scores[0]) == 1.5 and list(cids[0][1:5]) == [0, 1, 2, 3]
 
 
+@pytest.mark.parametrize("upload", ["sparse", "dense"])
 @pytest.mark.parametrize("scene", util.SCENES)
-def test_process_paf_golden(ek, scene):
-    """Reference peaks + nearest-upsampled PAF in, the compiled reference's subset out (bit-exact)."""
+def test_process_paf_golden(ek, scene, upload, monkeypatch):
+    """Reference peaks + nearest-upsampled PAF in, the compiled reference's subset out (bit-exact), both when
+    only the sampled PAF values are uploaded (default) and when the whole tensor is."""
+    monkeypatch.setenv("EKP_PROCESS_PAF_UPLOAD", upload)
     g = golden(scene)
     pk = g["ref_peaks"]
     h, w = g["heat"].shape[:2]
@@ -382,6 +385,21 @@ def test_overflow_is_reported(ek):
     small.close()
 
 
+def test_small_context_does_not_shrink_kernel_limits_of_a_big_one(ek):
+    """Kernel attributes (dynamic shared memory limits) are per device, not per context: creating a context
+    with small capacities after a big one must leave the big one working."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(2, 46, 54, (2, 3), seed=3)
+    big = ek.PostProcessor(device=0, max_batch=2, max_h=46, max_w=54, max_peaks=4096, max_humans=512)
+    big.run(_dev(heat), _dev(paf), frontend="dense")
+    want = big.results()["num_humans"].copy()
+    small = ek.PostProcessor(device=0, max_batch=1, max_h=8, max_w=8, max_peaks=16, max_humans=2)
+    big.run(_dev(heat), _dev(paf), frontend="dense")
+    assert np.array_equal(big.results()["num_humans"], want) and want.sum() > 0
+    small.close()
+    big.close()
+
+
 def test_argument_errors(ek, pp):
     from torch_ekpose_b200 import synthetic
     heat, paf = synthetic.make_batch(1, 46, 54, (1, 1), seed=1)
@@ -393,6 +411,17 @@ def test_argument_errors(ek, pp):
     big = _dev(np.zeros((65, 19, 5, 5), np.float32)), _dev(np.zeros((65, 38, 5, 5), np.float32))
     with pytest.raises(ek._lib.EkpError):
         pp.run(*big, frontend="dense")
+    # operator-surface tensors that are not 16-byte aligned are refused (they are written with 16-byte bulk copies)
+    hd, pd = _dev(heat), _dev(paf)
+    hm = torch.empty(368 * 432 * 19 + 4, dtype=torch.float32, device="cuda")
+    pm = torch.empty(368 * 432 * 38 + 4, dtype=torch.float32, device="cuda")
+    lib = ek._lib.lib
+    args = (pp._ctx, hd.data_ptr(), pd.data_ptr(), 1, 46, 54, ek._lib.LAYOUT_NCHW, 0.15, ek._lib.FRONTEND_DENSE)
+    rc = lib.ekp_postprocess(*args, hm.data_ptr() + 4, pm.data_ptr() + 4, 0)
+    assert rc == ek._lib.ERR_ARG and b"16-byte aligned" in lib.ekp_last_error()
+    rc = lib.ekp_postprocess(*args, hm.data_ptr(), pm.data_ptr(), 0)
+    assert rc == 0, lib.ekp_last_error()
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("people", [20, 50, 100, 150])

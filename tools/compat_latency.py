@@ -1,0 +1,46 @@
+"""Latency of the reference operator surface (host pointers): process_paf + the getter loop, per call, with the
+sparse upload (default) and with the whole paf_mat uploaded, next to the compiled reference on this box's CPU."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import oracle
+import torch_ekpose_b200 as ek
+from torch_ekpose_b200 import synthetic
+
+fe = oracle.Frontend()
+ref = oracle.RefPaf() if oracle.have_ref() else oracle.PortPaf()
+
+def getters(mod):
+    n = mod.get_num_humans()
+    for h in range(n):
+        for p in range(18):
+            c = mod.get_part_cid(h, p)
+            if c >= 0:
+                mod.get_part_x(c); mod.get_part_y(c); mod.get_part_score(c)
+        mod.get_score(h)
+    return n
+
+def run(label, h, w, people, seed):
+    heat, paf = synthetic.make_batch(1, h, w, people, seed=seed)
+    hw = np.ascontiguousarray(heat[0].transpose(1, 2, 0)); pw = np.ascontiguousarray(paf[0].transpose(1, 2, 0))
+    peaks = fe.ref_nms(hw)[None]
+    paf_up = fe.upsample_nearest(pw)
+    heat_up = np.zeros((8 * h, 8 * w, 19), np.float32)
+    out = []
+    for mode in ("sparse", "dense"):
+        os.environ["EKP_PROCESS_PAF_UPLOAD"] = mode
+        for _ in range(3): ek.pafprocess.process_paf(peaks, heat_up, paf_up)
+        t = time.perf_counter(); reps = 20
+        for _ in range(reps):
+            ek.pafprocess.process_paf(peaks, heat_up, paf_up); n = getters(ek.pafprocess)
+        out.append((mode, (time.perf_counter() - t) / reps * 1e3, n))
+    t = time.perf_counter(); reps = 5
+    for _ in range(reps):
+        sub, _ = oracle.subset_of(ref, peaks[0], 8 * h, 8 * w, paf_up)
+    tref = (time.perf_counter() - t) / reps * 1e3
+    print(f"{label}: {peaks.shape[1]} peaks, {out[0][2]} humans | ours sparse upload {out[0][1]:.3f} ms, whole tensor {out[1][1]:.3f} ms "
+          f"| reference C++ on this CPU {tref:.3f} ms (process_paf only)")
+
+run("368x432, 3 people", 46, 54, (3, 3), 1)
+run("656x368, 8 people", 46, 82, (8, 8), 2)
+run("1312x736, 35 people", 92, 164, (35, 35), 3)

@@ -377,8 +377,7 @@ static size_t assemble_smem(int max_humans, int conn_cap) {
 static int assemble_conn_cap(int max_peaks) { return 2 * max_peaks < 1536 ? 2 * max_peaks : 1536; }
 
 cudaError_t configure_assemble(int max_humans, int max_peaks) {
-    return cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) assemble_smem(max_humans, assemble_conn_cap(max_peaks)));
+    return raise_dynamic_smem_limit(assemble_kernel, assemble_smem(max_humans, assemble_conn_cap(max_peaks)));
 }
 
 cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,

@@ -35,6 +35,8 @@ cudaError_t configure_assemble(int max_humans, int max_peaks);
 cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,
                             int max_humans, int n, const unsigned* overflow, unsigned char* records, const ResultLayout& lay,
                             cudaStream_t stream);
+cudaError_t launch_pair_sample_offsets(const ekp_peak* line, const int* part_off, const int* pair_base, int H, int W, int C,
+                                       unsigned* offs, cudaStream_t stream);
 cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned* scratch, cudaStream_t stream);
 cudaError_t launch_preprocess(const unsigned char* src, float* out, const int* xofs, const short* ialpha, const int* yofs,
                               const short* ibeta, int n, int sh, int sw, int rh, int rw, int ph, int pw, int mode,
@@ -276,9 +278,13 @@ static int check_shape(const ekp_ctx* c, int n, int h, int w, int layout, const 
 }
 
 // stages 4-5 + result copies, shared by every entry point
-static int run_back_half(ekp_ctx* c, int n, int id_from_key, const PafSource& paf, int h1, cudaStream_t st) {
+static int run_peak_sort(ekp_ctx* c, int n, int id_from_key, cudaStream_t st) {
     mark(c, 1, st);
     CU(launch_peaks_sort(c->raw, c->raw_count, c->max_peaks, id_from_key, n, c->line, c->part_off, c->n_peaks, c->overflow, st));
+    c->launches += 1;
+    return EKP_OK;
+}
+static int run_connect_assemble(ekp_ctx* c, int n, const PafSource& paf, int h1, cudaStream_t st) {
     mark(c, 2, st);
     CU(launch_paf_connect(c->line, c->part_off, c->max_peaks, paf, h1, n, c->conns, c->n_conns, c->overflow, st));
     mark(c, 3, st);
@@ -286,11 +292,16 @@ static int run_back_half(ekp_ctx* c, int n, int id_from_key, const PafSource& pa
                        c->lay, st));
     mark(c, 4, st);
     if (c->timing) c->timed_runs++;
-    c->launches += 3;
+    c->launches += 2;
     CU(cudaMemcpyAsync(c->h_records, c->records, c->lay.stride * (size_t) n, cudaMemcpyDeviceToHost, st));  // one packed copy
     CU(cudaEventRecord(c->done, st));
     c->last_stream = st; c->last_n = n; c->has_run = true;
     return EKP_OK;
+}
+static int run_back_half(ekp_ctx* c, int n, int id_from_key, const PafSource& paf, int h1, cudaStream_t st) {
+    int rc = run_peak_sort(c, n, id_from_key, st);
+    if (rc) return rc;
+    return run_connect_assemble(c, n, paf, h1, st);
 }
 
 extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, int n, int h, int w, int layout,
@@ -300,6 +311,10 @@ extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, 
     if (!heat || !paf) return fail(EKP_ERR_ARG, "ekp_postprocess: NULL input");
     if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE) return fail(EKP_ERR_ARG, "ekp_postprocess: frontend %d", frontend);
     if (heat_mat && !paf_mat) return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat without paf_mat");
+    if ((reinterpret_cast<uintptr_t>(heat_mat) | reinterpret_cast<uintptr_t>(paf_mat)) & 15u)
+        return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat / paf_mat must be 16-byte aligned (they are written with 16-byte bulk copies)");
+    if ((reinterpret_cast<uintptr_t>(heat) | reinterpret_cast<uintptr_t>(paf)) & 3u)
+        return fail(EKP_ERR_ARG, "ekp_postprocess: heat / paf must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t) stream;
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
@@ -579,6 +594,11 @@ std::mutex g_mu;
 ekp_ctx* g_ctx = nullptr;
 float* g_dev_peaks = nullptr; size_t g_dev_peaks_cap = 0;
 float* g_dev_paf = nullptr; size_t g_dev_paf_cap = 0;
+// sparse upload: sample offsets (device + pinned host), gathered samples (pinned host + device), pair prefix
+unsigned* g_dev_offs = nullptr; unsigned* g_host_offs = nullptr; float2* g_host_samp = nullptr; float2* g_dev_samp = nullptr;
+size_t g_samp_cap = 0;
+int* g_dev_pair_base = nullptr;
+const long long kSparseMaxSamples = 8ll << 20;  // beyond this the whole tensor is uploaded instead
 std::vector<float> g_subset;      // [num_humans][20]
 std::vector<float> g_hscore;      // [num_humans] subset[18] / subset[19], computed on the device
 std::vector<ekp_peak> g_line;     // part-sorted peak table
@@ -615,19 +635,75 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
         const size_t pk_elems = (size_t) npk * p3, paf_elems = (size_t) f1 * f2 * f3;
         if (g_dev_peaks_cap < pk_elems) { if (g_dev_peaks) cudaFree(g_dev_peaks); g_dev_peaks = nullptr; g_dev_peaks_cap = 0;
             CU(cudaMalloc((void**) &g_dev_peaks, pk_elems * sizeof(float))); g_dev_peaks_cap = pk_elems; }
-        if (g_dev_paf_cap < paf_elems) { if (g_dev_paf) cudaFree(g_dev_paf); g_dev_paf = nullptr; g_dev_paf_cap = 0;
-            CU(cudaMalloc((void**) &g_dev_paf, paf_elems * sizeof(float))); g_dev_paf_cap = paf_elems; }
         cudaStream_t st = nullptr;
         const int npk_i = (int) npk;
+        // Sparse upload (default): stage 4 reads at most 10 positions of paf_mat per candidate pair, a few KB
+        // against the 24 MB tensor.  Pairs per limb follow from the part column of the caller's peaks.
+        int pair_base[EKP_NUM_LIMB + 1];
+        long long nsamples = 0;
+        bool sparse = paf_elems < (1ull << 32);
+        if (const char* e = getenv("EKP_PROCESS_PAF_UPLOAD")) sparse = sparse && strcmp(e, "dense") != 0;
+        if (sparse) {
+            int per_part[EKP_NUM_PART] = {0};
+            for (long long k = 0; k < npk; k++) {
+                const float pt = peaks[k * p3 + 4];
+                const int part = pt > -1.f && pt < (float) EKP_NUM_PART ? (int) pt : -1;  // (int) truncates like the ingest kernel;
+                if (part >= 0) per_part[part]++;  // any peak it rejects for another reason fails the whole call (EKP_OVF_BADPEAK)
+            }
+            static const int pairs[EKP_NUM_LIMB][2] = {{1, 2}, {1, 5}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {1, 8}, {8, 9}, {9, 10}, {1, 11},
+                                                       {11, 12}, {12, 13}, {1, 0}, {0, 14}, {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17}};
+            long long acc = 0;
+            for (int l = 0; l < EKP_NUM_LIMB; l++) {
+                pair_base[l] = (int) acc;
+                acc += (long long) std::min(per_part[pairs[l][0]], EKP_MAX_PART) * std::min(per_part[pairs[l][1]], EKP_MAX_PART);
+            }
+            pair_base[EKP_NUM_LIMB] = (int) acc;
+            nsamples = acc * 10;
+            sparse = nsamples <= kSparseMaxSamples;
+        }
         CU(cudaMemcpyAsync(g_dev_peaks, peaks, pk_elems * sizeof(float), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(g_dev_paf, pafmap, paf_elems * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
         mark(c, 0, st);
         CU(launch_peaks_ingest(g_dev_peaks, nullptr, npk_i, npk_i, p3, 1, f2, f1, c->raw, c->raw_count, c->max_peaks, c->overflow, st));
         c->launches += 1;
         PafSource src;
-        src.ptr = g_dev_paf; src.mode = PAF_FULL_HWC; src.layout = EKP_LAYOUT_NHWC; src.H = f1; src.W = f2; src.C = f3; src.h = f1 / 8; src.w = f2 / 8;
-        rc = run_back_half(c, 1, /*id_from_key=*/1, src, h1, st);
+        src.layout = EKP_LAYOUT_NHWC; src.H = f1; src.W = f2; src.C = f3; src.h = f1 / 8; src.w = f2 / 8; src.pair_base = nullptr;
+        rc = run_peak_sort(c, 1, /*id_from_key=*/1, st);
+        if (rc) return rc;
+        if (sparse && nsamples > 0) {
+            if (g_samp_cap < (size_t) nsamples) {
+                if (g_dev_offs) cudaFree(g_dev_offs);
+                if (g_dev_samp) cudaFree(g_dev_samp);
+                if (g_host_offs) cudaFreeHost(g_host_offs);
+                if (g_host_samp) cudaFreeHost(g_host_samp);
+                g_dev_offs = nullptr; g_dev_samp = nullptr; g_host_offs = nullptr; g_host_samp = nullptr; g_samp_cap = 0;
+                const size_t cap = (size_t) nsamples + (size_t) nsamples / 2 + 1024;
+                CU(cudaMalloc((void**) &g_dev_offs, cap * sizeof(unsigned)));
+                CU(cudaMalloc((void**) &g_dev_samp, cap * sizeof(float2)));
+                CU(cudaMallocHost((void**) &g_host_offs, cap * sizeof(unsigned)));
+                CU(cudaMallocHost((void**) &g_host_samp, cap * sizeof(float2)));
+                g_samp_cap = cap;
+            }
+            if (!g_dev_pair_base) CU(cudaMalloc((void**) &g_dev_pair_base, sizeof(int) * (EKP_NUM_LIMB + 1)));
+            CU(cudaMemcpyAsync(g_dev_pair_base, pair_base, sizeof(pair_base), cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(g_dev_offs, 0, (size_t) nsamples * sizeof(unsigned), st));  // limbs the kernel skips stay in bounds
+            CU(launch_pair_sample_offsets(c->line, c->part_off, g_dev_pair_base, f1, f2, f3, g_dev_offs, st));
+            c->launches += 1;
+            CU(cudaMemcpyAsync(g_host_offs, g_dev_offs, (size_t) nsamples * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (long long k = 0; k < nsamples; k++) {  // the gather: a copy, no arithmetic
+                const float* q = pafmap + g_host_offs[k];
+                g_host_samp[k] = make_float2(q[0], q[1]);
+            }
+            CU(cudaMemcpyAsync(g_dev_samp, g_host_samp, (size_t) nsamples * sizeof(float2), cudaMemcpyHostToDevice, st));
+            src.ptr = reinterpret_cast<const float*>(g_dev_samp); src.mode = PAF_PACKED; src.pair_base = g_dev_pair_base;
+        } else {
+            if (g_dev_paf_cap < paf_elems) { if (g_dev_paf) cudaFree(g_dev_paf); g_dev_paf = nullptr; g_dev_paf_cap = 0;
+                CU(cudaMalloc((void**) &g_dev_paf, paf_elems * sizeof(float))); g_dev_paf_cap = paf_elems; }
+            CU(cudaMemcpyAsync(g_dev_paf, pafmap, paf_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+            src.ptr = g_dev_paf; src.mode = PAF_FULL_HWC;
+        }
+        rc = run_connect_assemble(c, 1, src, h1, st);
         if (rc) return rc;
         std::vector<ekp_peak> line((size_t) c->max_peaks);
         std::vector<float> subset((size_t) c->max_humans * 20);

@@ -32,7 +32,9 @@ struct __align__(16) Conn {  // pafprocess.h:45-51, plus the two score sums the 
 enum PafMode {
     PAF_FULL_HWC = 0,      // gather from a materialised full-resolution [H][W][C] tensor
     PAF_LO_NEAREST = 1,    // paf_lo[y>>3][x>>3]   (== cv2 INTER_NEAREST x8, paf_to_pose.py:356-357)
-    PAF_LO_BILINEAR = 2    // bilinear x8 of paf_lo, same arithmetic as the materialising kernel
+    PAF_LO_BILINEAR = 2,   // bilinear x8 of paf_lo, same arithmetic as the materialising kernel
+    PAF_PACKED = 3         // the samples themselves, gathered beforehand: float2 [(pair_base[limb] + pair) * 10 + i]
+                           // (host-pointer process_paf: only the values stage 4 reads are uploaded)
 };
 
 struct PafSource {
@@ -41,6 +43,7 @@ struct PafSource {
     int layout;        // of the stride-8 tensor (EKP_LAYOUT_*)
     int H, W, C;       // full-resolution dims and channel count
     int h, w;          // stride-8 dims (modes 1, 2)
+    const int* pair_base;  // [20] prefix of nA*nB over the limbs (mode 3)
 };
 
 // pafprocess.h:16-24
@@ -77,6 +80,17 @@ __device__ __forceinline__ float lo_at(const float* lo, int layout, int img, int
 struct ResultLayout {
     size_t stride, off_subset, off_hparts, off_hscore;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and device, shared by every context: a context with
+// smaller capacities must never LOWER it under a bigger one.  Raises the limit to `bytes` if it is below.
+template <typename Kernel>
+inline cudaError_t raise_dynamic_smem_limit(Kernel kernel, size_t bytes) {
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
+    if (e != cudaSuccess) return e;
+    if ((size_t) attr.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
 
 // launch parameter blocks --------------------------------------------------------------------
 struct DenseParams {

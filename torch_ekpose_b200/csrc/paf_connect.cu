@@ -50,9 +50,15 @@ __device__ __forceinline__ Sample2 pair_at(const float* q, int ch1, int ch2) {
     return r;
 }
 
+// `packed` = index of this sample in the pre-gathered list (PAF_PACKED only)
 template <bool kVec2>
-__device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int ly, int lx, int ch1, int ch2) {
+__device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int ly, int lx, int ch1, int ch2, long long packed) {
     Sample2 r;
+    if (s.mode == PAF_PACKED) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(s.ptr) + packed);
+        r.x = v.x; r.y = v.y;
+        return r;
+    }
     lx = min(max(lx, 0), s.W - 1);  // memory safety only: valid peaks never sample outside
     ly = min(max(ly, 0), s.H - 1);
     if (s.mode == PAF_FULL_HWC) {
@@ -91,7 +97,8 @@ __device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int l
 // float operations of score_pair; false when all four are <= 0.05 (then at most 6 of 10 can pass) or the
 // two peaks coincide (:66).
 template <bool kVec2>
-__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1, int ch2) {
+__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1, int ch2,
+                                              long long packed0) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
     float vx = (float) dxi, vy = (float) dyi;
     const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
@@ -106,7 +113,7 @@ __device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak&
         const int i = 3 + k;
         const int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);
         const int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
-        sv[k] = paf_sample<kVec2>(paf, img, ly, lx, ch1, ch2);
+        sv[k] = paf_sample<kVec2>(paf, img, ly, lx, ch1, ch2, packed0 + i);
     }
     bool any = false;
 #pragma unroll
@@ -117,7 +124,7 @@ __device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak&
 // pafprocess.cpp:59-94 for one (a, b) pair.  Returns true when the pair becomes a candidate.
 template <bool kVec2>
 __device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1,
-                                           int ch2, int h1, float& criterion2) {
+                                           int ch2, int h1, float& criterion2, long long packed0) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
     float vx = (float) dxi, vy = (float) dyi;
     const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
@@ -134,7 +141,7 @@ __device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b,
     }
     Sample2 sv[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kVec2>(paf, img, ly[i], lx[i], ch1, ch2);  // independent gathers in flight
+    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kVec2>(paf, img, ly[i], lx[i], ch1, ch2, packed0 + i);  // independent gathers in flight
     float scores = 0.0f;
     int criterion1 = 0;
 #pragma unroll
@@ -368,6 +375,14 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     // ---- stage 4: score all nA x nB pairs; candidates end up in pair order (a outer, b inner) --------
     PROF_MARK(0);  // peaks staged
     const int npairs = nA * nB;
+    long long packed_base = 0;  // PAF_PACKED (one image): where this limb's samples start in the pre-gathered list
+    if (paf.mode == PAF_PACKED) {
+        packed_base = paf.pair_base[limb];
+        if (npairs != paf.pair_base[limb + 1] - paf.pair_base[limb]) {  // the list was laid out for other counts: refuse
+            if (threadIdx.x == 0) { *out_n = 0; atomicOr(overflow + img, EKP_OVF_BADPEAK); }
+            return;
+        }
+    }
     int total = 0;  // candidates so far, identical in every thread
     // Few pairs (every scene but a crowd): one pass, one round trip to memory.  Otherwise pass 1 thins them out.
     const bool two_pass = npairs > 2 * kConnThreads;
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
             bool keep = false;
             if (pidx < win_end) {
                 const int ia = pidx / nB;
-                keep = pair_may_pass<kVec2>(sA[ia], sB[pidx - ia * nB], paf, img, ch1, ch2);
+                keep = pair_may_pass<kVec2>(sA[ia], sB[pidx - ia * nB], paf, img, ch1, ch2, (packed_base + pidx) * 10);
             }
             const int pos = ordered_slot(keep, sWarpCnt, nsurv);
             if (keep) sTag2[pos] = (unsigned) pidx;
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
                 const int pidx = (int) sTag2[k];
                 ia = pidx / nB;
                 ib = pidx - ia * nB;
-                pass = score_pair<kVec2>(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit);
+                pass = score_pair<kVec2>(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit, (packed_base + pidx) * 10);
             }
             const int pos = ordered_slot(pass, sWarpCnt, total);
             if (pass && pos < EKP_MAX_CAND) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
@@ -491,6 +506,44 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
 #endif
 }
 
+// ---- host-pointer process_paf: which elements of the caller's paf_mat does stage 4 read? ---------------
+// One block per limb of ONE image: for every pair (a outer, b inner) and sample i the element offset of
+// channel ch1 at the sample position (roundpaf of pafprocess.cpp:228-233, clamped like paf_sample).  The host
+// gathers the two floats at each offset (ch2 == ch1 + 1) and uploads only those; the connect kernel then
+// runs in PAF_PACKED mode on identical values.
+__global__ void __launch_bounds__(kConnThreads) pair_sample_offsets_kernel(const ekp_peak* __restrict__ line,
+                                                                           const int* __restrict__ part_off,
+                                                                           const int* __restrict__ pair_base, int H, int W, int C,
+                                                                           unsigned* __restrict__ offs) {
+    const int limb = blockIdx.x;
+    const int pa = kPairs[limb][0], pb = kPairs[limb][1];
+    const int ch1 = kPairsNet[limb][0];
+    const int offA = part_off[pa], offB = part_off[pb];
+    const int nA = min(part_off[pa + 1] - offA, EKP_MAX_PART), nB = min(part_off[pb + 1] - offB, EKP_MAX_PART);
+    const int npairs = nA * nB;
+    if (npairs != pair_base[limb + 1] - pair_base[limb]) return;  // the host counted differently: it will not use the list
+    unsigned* out = offs + (size_t) pair_base[limb] * 10;
+    for (int pidx = threadIdx.x; pidx < npairs; pidx += kConnThreads) {
+        const int ia = pidx / nB;
+        const ekp_peak a = line[offA + ia], b = line[offB + (pidx - ia * nB)];
+        const float step_x = __fdiv_rn((float) (b.x - a.x), 10.0f);
+        const float step_y = __fdiv_rn((float) (b.y - a.y), 10.0f);
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);
+            int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
+            lx = min(max(lx, 0), W - 1);
+            ly = min(max(ly, 0), H - 1);
+            out[(size_t) pidx * 10 + i] = (unsigned) (((size_t) ly * W + lx) * C + ch1);
+        }
+    }
+}
+cudaError_t launch_pair_sample_offsets(const ekp_peak* line, const int* part_off, const int* pair_base, int H, int W, int C,
+                                       unsigned* offs, cudaStream_t stream) {
+    pair_sample_offsets_kernel<<<EKP_NUM_LIMB, kConnThreads, 0, stream>>>(line, part_off, pair_base, H, W, C, offs);
+    return cudaGetLastError();
+}
+
 // Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one warp), so that the tie permutation -- including the heapsort fallback, which real scenes never
 // reach -- can be compared with the compiled reference's std::sort.
 __global__ void debug_std_sort_kernel(float* scores, unsigned* tags, int n, unsigned* scratch) {
@@ -507,7 +560,7 @@ cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int ma
                                int n, Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream) {
     dim3 grid(EKP_NUM_LIMB, n);
     // both PAF channels of a limb with one 8-byte load: channel-last tensor, even channel count, aligned base
-    const bool channel_last = paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC;
+    const bool channel_last = paf.mode != PAF_PACKED && (paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC);
     const bool vec2 = channel_last && paf.C % 2 == 0 && reinterpret_cast<uintptr_t>(paf.ptr) % 8 == 0;
     if (vec2) paf_connect_kernel<true><<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);
     else paf_connect_kernel<false><<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);

@@ -102,8 +102,7 @@ cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fi
 }
 
 cudaError_t configure_peaks_sort(int raw_cap) {
-    return cudaFuncSetAttribute(peaks_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) (sizeof(unsigned long long) * (size_t) raw_cap));
+    return raise_dynamic_smem_limit(peaks_sort_kernel, sizeof(unsigned long long) * (size_t) raw_cap);
 }
 
 cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int id_from_key, int n, ekp_peak* line,
