@@ -165,7 +165,10 @@ long long ekp_kernel_launches(const ekp_ctx *ctx); /* kernels launched by this c
  * through h1 and is never read (as in the reference, pafprocess.cpp:83) so it may be NULL;
  * pafmap [f1,f2,f3].  Runs on the device selected by EKP_DEVICE (default 0).  Unlike the
  * reference (always 0, undefined behaviour on bad input) a negative ekp_status is returned
- * when the input is invalid or no GPU is available. */
+ * when the input is invalid or no GPU is available.
+ * Only what stage 4 reads of pafmap crosses the bus: a kernel lists the <= 10 sample positions of every
+ * candidate pair, the two floats at each position are gathered from the caller's array and uploaded
+ * (environment EKP_PROCESS_PAF_UPLOAD=dense uploads the whole tensor instead). */
 int process_paf(int p1, int p2, int p3, float *peaks, int h1, int h2, int h3, float *heatmap, int f1, int f2,
                 int f3, float *pafmap);
 int get_num_humans(void);
