@@ -38,6 +38,17 @@ def run(label, h, w, people, seed):
     for _ in range(reps):
         sub, _ = oracle.subset_of(ref, peaks[0], 8 * h, 8 * w, paf_up)
     tref = (time.perf_counter() - t) / reps * 1e3
+    # route 2: the whole of paf_to_pose_cpp (numpy HWC in, list[Human] out) on the GPU, one image per call
+    for _ in range(3): ek.paf_to_pose_cpp(hw, pw, ek.cfg)
+    t = time.perf_counter(); reps = 20
+    for _ in range(reps): humans = ek.paf_to_pose_cpp(hw, pw, ek.cfg)
+    t2 = (time.perf_counter() - t) / reps * 1e3
+    t = time.perf_counter(); reps = 5
+    for _ in range(reps):
+        pk = fe.ref_nms(hw); up = fe.upsample_nearest(pw); fe.upsample_nearest(hw); oracle.subset_of(ref, pk, 8 * h, 8 * w, up)
+    t2ref = (time.perf_counter() - t) / reps * 1e3
+    print(f"{label}: paf_to_pose_cpp one image: ours {t2:.3f} ms ({len(humans)} humans) | CPU path (C restatement of NMS + nearest x8 + "
+          f"reference process_paf) {t2ref:.3f} ms")
     print(f"{label}: {peaks.shape[1]} peaks, {out[0][2]} humans | ours sparse upload {out[0][1]:.3f} ms, whole tensor {out[1][1]:.3f} ms "
           f"| reference C++ on this CPU {tref:.3f} ms (process_paf only)")
 
