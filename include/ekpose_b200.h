@@ -155,6 +155,7 @@ int ekp_set_timing(ekp_ctx *ctx, int enable);
 int ekp_stage_times(ekp_ctx *ctx, float *ms, int *runs);
 
 /* Introspection for tests and the benchmark. */
+int ekp_last_batch(const ekp_ctx *ctx);   /* images of the last submitted run = rows the ekp_results* calls write */
 int ekp_max_batch(const ekp_ctx *ctx);
 int ekp_max_peaks(const ekp_ctx *ctx);
 int ekp_max_humans(const ekp_ctx *ctx);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ekp_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ekp_set_timing": (_i, [_vp, _i]),
     "ekp_stage_times": (_i, [_vp, _vp, _vp]),
+    "ekp_last_batch": (_i, [_vp]),
     "ekp_max_batch": (_i, [_vp]),
     "ekp_max_peaks": (_i, [_vp]),
     "ekp_max_humans": (_i, [_vp]),

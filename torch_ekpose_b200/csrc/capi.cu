@@ -239,6 +239,7 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
 }
 
 extern "C" void ekp_destroy(ekp_ctx* ctx) { ctx_free(ctx); }
+extern "C" int ekp_last_batch(const ekp_ctx* c) { return c && c->has_run ? c->last_n : 0; }
 extern "C" int ekp_max_batch(const ekp_ctx* c) { return c ? c->max_batch : 0; }
 extern "C" int ekp_max_peaks(const ekp_ctx* c) { return c ? c->max_peaks : 0; }
 extern "C" int ekp_max_humans(const ekp_ctx* c) { return c ? c->max_humans : 0; }

@@ -153,11 +153,16 @@ class PostProcessor:
         self._n, self._hw = n, (H // 8, W // 8)
 
     # ------------------------------------------------------------------------------------------
+    def _rows(self) -> int:
+        """Images the library will write results for (its own count of the last run, so that the arrays handed to
+        it can never be too small, whoever submitted that run)."""
+        return int(_lib.lib.ekp_last_batch(self._ctx))
+
     def results(self, with_peaks: bool = False) -> dict:
         """Wait and return numpy tables: num_humans [n], subset [n, max_humans, 20] (float32, the
         reference's rows), n_peaks [n], overflow [n] and optionally peaks [n, max_peaks]
         (structured x, y, score, id) + part_off [n, 19]."""
-        n = self._n
+        n = self._rows()
         num = np.zeros(n, np.int32)
         npk = np.zeros(n, np.int32)
         ovf = np.zeros(n, np.uint32)
@@ -177,7 +182,7 @@ class PostProcessor:
     def human_tables(self):
         """(num_humans [n], parts [n, max_humans, 18] structured (x, y, score, id; id -1 = absent),
         scores [n, max_humans]) -- the whole getter loop of paf_to_pose_cpp in three arrays."""
-        n = self._n
+        n = self._rows()
         num = np.zeros(n, np.int32)
         parts = np.zeros((n, self.max_humans, _lib.NUM_PART), _PEAK_DT)
         scores = np.zeros((n, self.max_humans), np.float32)
@@ -190,7 +195,7 @@ class PostProcessor:
         h, w = self._hw
         H, W = 8 * h, 8 * w
         out = []
-        for i in range(self._n):
+        for i in range(len(num)):
             humans = []
             for k in range(int(num[i])):
                 human = Human([])
