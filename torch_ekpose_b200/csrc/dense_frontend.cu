@@ -92,7 +92,17 @@ constexpr int kPafRows = kTB + 1;   // rows staged for the tile's bilinear row p
 // Vertical taps of an interior row (no reflect / clamp influence) depend only on Y & 7.
 __constant__ float cTapsInterior[8][8];
 
-cudaError_t set_interior_taps(const float* taps64) { return cudaMemcpyToSymbol(cTapsInterior, taps64, sizeof(float) * 64); }
+// cTapsInteriorMax[j] = max over the 8 phases of cTapsInterior[.][j]: the most row j of the window can weigh
+__constant__ float cTapsInteriorMax[8];
+
+cudaError_t set_interior_taps(const float* taps64) {
+    float mx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 8; k++)
+        for (int j = 0; j < 8; j++) mx[j] = taps64[k * 8 + j] > mx[j] ? taps64[k * 8 + j] : mx[j];
+    cudaError_t e = cudaMemcpyToSymbol(cTapsInterior, taps64, sizeof(float) * 64);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(cTapsInteriorMax, mx, sizeof(mx));
+    return e;
+}
 
 // floor(n / d) == __umulhi(n, magic_of(d)) for n * d < 2^32 (32-bit divide only: no 64-bit division subroutine)
 __host__ __device__ __forceinline__ unsigned magic_of(unsigned d) { return 0xFFFFFFFFu / d + 1u; }
@@ -371,11 +381,17 @@ __device__ __forceinline__ void build_colmax(const TileGeom& g, const float* sHe
 // produce is a convex combination of the staged stride-8 samples in columns
 // [bx(first lane), bx(last lane) + 4]: if their maximum (sColMax, over all staged rows) is below
 // the threshold by more than the rounding slack of ten float operations, no pixel there can
-// pass `S > thr`, hence no peak, and the strip is never visited.  Survivors go to a compact
-// list that the warps then share evenly.
+// pass `S > thr`, hence no peak, and the strip is never visited.
+// Strips that pass this cheap test get a sharper one, row block by row block: with M_j the maximum (>= 0) of
+// window row j over the strip's columns, the horizontal pass gives T_j <= M_j for every lane, so a pixel of an
+// interior row block is at most sum_j max_phase(tap_j) * M_j -- the outer rows of the window weigh a few
+// percent, so a blob two cells above or below the tile no longer activates it (about half of the tasks).
+// Border blocks (reflected taps) keep the plain maximum.  Survivors go to a compact list that the warps share.
 template <bool kDebug>
-__device__ __forceinline__ void build_task_list(const DenseParams& p, const TileGeom& g, const TileCtl& ctl, int tid, int nthr) {
-    const int w = p.w, W = 8 * w, TW = 8 * g.twl, X0 = 8 * g.i0;
+__device__ __forceinline__ void build_task_list(const DenseParams& p, const TileGeom& g, const float* sHeat, const TileCtl& ctl,
+                                                int tid, int nthr) {
+    const int h = p.h, w = p.w, W = 8 * w, TW = 8 * g.twl, X0 = 8 * g.i0;
+    const int hcols = p.tile_wl + 6;
     const int nstrips = (TW + 29) / 30;
     const unsigned m_strips = magic_of(nstrips);
     const int ntask = EKP_NUM_PART * nstrips;
@@ -390,6 +406,24 @@ __device__ __forceinline__ void build_task_list(const DenseParams& p, const Tile
             float mx = 0.f;
             for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, ctl.colmax[(i - g.hc0) * EKP_HEAT_CH + c]);
             active = mx > p.thr * 0.99999f;
+            if (active) {
+                bool any = false;
+                for (int b = 0; b < g.tb && !any; b++) {
+                    const int m = g.m0 + b;
+                    const int wb = min(max(m - 2, 0), h - 5);
+                    const bool interior = m >= 2 && m <= h - 3;
+                    float bound = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        const float* row = sHeat + ((wb + j - g.hr0) * hcols - g.hc0) * EKP_HEAT_CH + c;
+                        float mj = 0.f;
+                        for (int i = c_lo; i <= c_hi; i++) mj = fmaxf(mj, row[i * EKP_HEAT_CH]);
+                        bound = interior ? fmaf(cTapsInteriorMax[j], mj, bound) : fmaxf(bound, mj);
+                    }
+                    any = bound > p.thr * 0.9999f;
+                }
+                active = any;
+            }
         }
         if (active) ctl.list[atomicAdd(ctl.num_active, 1)] = (unsigned short) t;
     }
@@ -531,7 +565,7 @@ __device__ __forceinline__ void process_tile_lean(const DenseParams& p, const Ti
         build_colmax(g, sm.heat, hcols, ctl.colmax, threadIdx.x, kLeanThreads);
         __syncthreads();
     }
-    build_task_list<kDebug>(p, g, ctl, threadIdx.x, kLeanThreads);
+    build_task_list<kDebug>(p, g, sm.heat, ctl, threadIdx.x, kLeanThreads);
     __syncthreads();
     nms_task_loop<kDebug>(p, g, sm.heat, ctl);
 }
@@ -573,7 +607,7 @@ __device__ __forceinline__ void process_tile_mat(const DenseParams& p, const Til
         bar_sync(BAR_NMS, kNmsThreads);
         build_colmax(g, sm.heat, hcols, ctl.colmax, t, kNmsThreads);
         bar_sync(BAR_NMS, kNmsThreads);
-        build_task_list<false>(p, g, ctl, t, kNmsThreads);
+        build_task_list<false>(p, g, sm.heat, ctl, t, kNmsThreads);
         __threadfence_block();
         bar_sync(BAR_NMS, kNmsThreads);     // list and count complete for this group ...
         bar_arrive(BAR_HEAT_READY, kMatThreads);  // ... and published to the fill warps
