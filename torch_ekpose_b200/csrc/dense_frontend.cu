@@ -43,7 +43,7 @@ namespace ekp {
 #define EKP_LEAN_THREADS 256
 #endif
 #ifndef EKP_LEAN_BLOCKS
-#define EKP_LEAN_BLOCKS 3
+#define EKP_LEAN_BLOCKS 5
 #endif
 #ifndef EKP_MAT_THREADS
 #define EKP_MAT_THREADS 384
