@@ -49,7 +49,10 @@ typedef enum ekp_layout { EKP_LAYOUT_NCHW = 0, EKP_LAYOUT_NHWC = 1 } ekp_layout;
 /* which peak front-end runs as stages 1-3 */
 typedef enum ekp_frontend {
     EKP_FRONTEND_DENSE = 0,     /* bilinear x8 -> Gaussian sigma 3 -> 3x3 max NMS (BASELINE.json north_star) */
-    EKP_FRONTEND_REFERENCE = 1  /* the reference's NMS(): stride-8 cross NMS + bicubic patch refinement */
+    EKP_FRONTEND_REFERENCE = 1, /* the reference's NMS(): stride-8 cross NMS + bicubic patch refinement */
+    EKP_FRONTEND_REFERENCE_COARSE = 2 /* NMS(bool_refine_center=False) / find_peaks (paf_to_pose.py:26-36, :119-122): the
+                                       * stride-8 maxima themselves, reported at (8c + 3) = (int) compute_resized_coords(c, 8)
+                                       * (:39-57, truncated like pafprocess.cpp:30-31) with the heat value as score */
 } ekp_frontend;
 
 /* per-image overflow bits reported by ekp_results */

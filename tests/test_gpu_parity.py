@@ -160,6 +160,58 @@ def test_nms_dropin(ek):
     assert_bits_equal(flat, g["ref_peaks"], "NMS joint list")
 
 
+def _find_peaks_reference(param, img):
+    """The reference's own expression, paf_to_pose.py:34-36 (SciPy is the primitive it imports, :4-6)."""
+    from scipy.ndimage import generate_binary_structure, maximum_filter
+    peaks_binary = (maximum_filter(img, footprint=generate_binary_structure(2, 1)) == img) * (img > param)
+    return np.array(np.nonzero(peaks_binary)[::-1]).T
+
+
+def test_find_peaks_dropin(ek):
+    """find_peaks: plateaus give several peaks, borders compare with in-bounds neighbours only."""
+    rng = np.random.default_rng(3)
+    for shape, levels in [((46, 54), None), ((23, 31), 6), ((5, 5), 3), ((92, 164), 40)]:
+        img = rng.random(shape).astype(np.float32)
+        if levels:
+            img = (np.floor(img * levels) / levels).astype(np.float32)   # exact ties, plateaus
+        for thr in (0.15, 0.5, -1.0):
+            got = ek.find_peaks(thr, img)
+            want = _find_peaks_reference(np.float32(thr), img)
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, levels, thr)
+    assert np.array_equal(ek.compute_resized_coords([1, 2], 2), [2.5, 4.5])     # the example of paf_to_pose.py:43-44
+
+
+@pytest.mark.parametrize("scene", ["c2_46x54_p6", "c4_crowd_64x96_p24", "empty_46x54"])
+def test_nms_without_refinement_and_people(ek, scene):
+    """NMS(bool_refine_center=False) (paf_to_pose.py:119-125) and the people stages 4-5 build from those peaks."""
+    g = golden(scene)
+    heat, paf = g["heat"], g["paf"]
+    lists = ek.NMS(heat, upsampFactor=8, bool_refine_center=False, config=ek.cfg)
+    want, cnt = [], 0
+    for k in range(18):
+        pk = _find_peaks_reference(np.float32(0.15), heat[:, :, k])
+        arr = np.zeros((len(pk), 4))
+        for i, p_ in enumerate(pk):
+            arr[i] = tuple(ek.compute_resized_coords(p_, 8)) + (heat[p_[1], p_[0], k], cnt)
+            cnt += 1
+        want.append(arr)
+    for k in range(18):
+        assert lists[k].shape == want[k].shape and np.array_equal(lists[k], want[k]), k
+    h, w = heat.shape[:2]
+    pp2 = ek.PostProcessor(device=0, max_batch=1, max_h=h, max_w=w, max_peaks=2048, max_humans=128)
+    pp2.run(heat[None], paf[None], layout="nhwc", frontend="reference_coarse")
+    res = pp2.results()
+    pp2.close()
+    peaks = np.array([tuple(r) + (k,) for k, rows in enumerate(want) for r in rows], np.float32).reshape(-1, 5)
+    if len(peaks):
+        sub, _ = util.oracle_people(peaks, 8 * h, 8 * w, util.frontend().upsample_nearest(paf))
+    else:
+        sub = np.zeros((0, 20), np.float32)
+    m = int(res["num_humans"][0])
+    assert m == len(sub)
+    assert_bits_equal(res["subset"][0, :m], sub, "subset")
+
+
 # ---------------------------------------------------------------------------------------------
 # dense front-end (north_star stages 1-3) + stages 4-5
 # ---------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("EKPOSE_B200_SO") or os.path.join(HERE, "libekpose_b200
 
 NUM_PART, NUM_LIMB, HEAT_CH, PAF_CH, UP, SUBSET_COLS = 18, 19, 19, 38, 8, 20
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-FRONTEND_DENSE, FRONTEND_REFERENCE = 0, 1
+FRONTEND_DENSE, FRONTEND_REFERENCE, FRONTEND_REFERENCE_COARSE = 0, 1, 2
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
 OVF_PEAKS, OVF_PART, OVF_CANDIDATES, OVF_HUMANS, OVF_BADPEAK = 1, 2, 4, 8, 16
 

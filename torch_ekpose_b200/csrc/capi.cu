@@ -310,7 +310,8 @@ extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, 
     int rc = check_shape(c, n, h, w, layout, "ekp_postprocess");
     if (rc) return rc;
     if (!heat || !paf) return fail(EKP_ERR_ARG, "ekp_postprocess: NULL input");
-    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE) return fail(EKP_ERR_ARG, "ekp_postprocess: frontend %d", frontend);
+    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE && frontend != EKP_FRONTEND_REFERENCE_COARSE)
+        return fail(EKP_ERR_ARG, "ekp_postprocess: frontend %d", frontend);
     if (heat_mat && !paf_mat) return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat without paf_mat");
     if ((reinterpret_cast<uintptr_t>(heat_mat) | reinterpret_cast<uintptr_t>(paf_mat)) & 15u)
         return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat / paf_mat must be 16-byte aligned (they are written with 16-byte bulk copies)");
@@ -341,6 +342,7 @@ extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, 
         RefParams p;
         p.heat = heat; p.n = n; p.h = h; p.w = w; p.layout = layout; p.thr = thr_heat;
         p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.cubic = c->cubic;
+        p.refine = frontend == EKP_FRONTEND_REFERENCE ? 1 : 0;
         CU(launch_ref_frontend(p, st));
         c->launches += 1;
         if (paf_mat) { CU(launch_upsample_nearest(paf, layout, n, h, w, EKP_PAF_CH, paf_mat, st)); c->launches += 1; }

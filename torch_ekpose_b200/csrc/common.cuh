@@ -117,6 +117,7 @@ struct RefParams {
     int* raw_count;
     int raw_cap;
     const float* cubic; // [8][4] cv2 bicubic coefficients for t = (2k+1)/16
+    int refine;         // 0: report the stride-8 maxima themselves (NMS(bool_refine_center=False), paf_to_pose.py:119-122)
 };
 
 }  // namespace ekp

@@ -42,6 +42,21 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_frontend_kernel(const RefP
             if (is_max && y < h - 1) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y + 1, x) > v);
         }
         unsigned mask = __ballot_sync(0xffffffffu, is_max);
+        if (!p.refine) {  // bool_refine_center=False: the maxima themselves, at (c + 0.5) * 8 - 0.5 truncated, heat value as score
+            if (is_max) {
+                const int slot = atomicAdd(p.raw_count + img, 1);
+                if (slot < p.raw_cap) {
+                    RawPeak pk;
+                    pk.x = 8 * x + 3;
+                    pk.y = 8 * y + 3;
+                    pk.score = lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x);
+                    pk.part = part;
+                    pk.key = ((unsigned) y << 16) | (unsigned) x;
+                    p.raw[(size_t) img * p.raw_cap + slot] = pk;
+                }
+            }
+            continue;
+        }
         while (mask) {  // the whole warp refines one peak at a time
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;

@@ -33,7 +33,8 @@ except Exception:  # pragma: no cover
     torch = None
 
 _PEAK_DT = np.dtype([("x", np.int32), ("y", np.int32), ("score", np.float32), ("id", np.int32)])
-_FRONTENDS = {"dense": _lib.FRONTEND_DENSE, "reference": _lib.FRONTEND_REFERENCE}
+_FRONTENDS = {"dense": _lib.FRONTEND_DENSE, "reference": _lib.FRONTEND_REFERENCE,
+              "reference_coarse": _lib.FRONTEND_REFERENCE_COARSE}
 _LAYOUTS = {"nchw": _lib.LAYOUT_NCHW, "nhwc": _lib.LAYOUT_NHWC}
 
 
@@ -103,7 +104,7 @@ class PostProcessor:
         """Submit one batch (n <= max_batch).  CUDA tensors take the device entry point; NumPy
         arrays / CPU tensors take the host entry point (H2D copies on the same stream)."""
         if frontend not in _FRONTENDS:
-            raise ValueError("frontend must be 'dense' or 'reference'")
+            raise ValueError("frontend must be 'dense', 'reference' or 'reference_coarse'")
         n, h, w = self._dims(heat.shape, paf.shape, layout)
         st = self._stream(stream)
         thr = float(np.float32(thr))
@@ -158,7 +159,7 @@ class PostProcessor:
         it can never be too small, whoever submitted that run)."""
         return int(_lib.lib.ekp_last_batch(self._ctx))
 
-    def results(self, with_peaks: bool = False) -> dict:
+    def results(self, with_peaks: bool = False, raise_on_overflow: bool = True) -> dict:
         """Wait and return numpy tables: num_humans [n], subset [n, max_humans, 20] (float32, the
         reference's rows), n_peaks [n], overflow [n] and optionally peaks [n, max_peaks]
         (structured x, y, score, id) + part_off [n, 19]."""
@@ -170,7 +171,8 @@ class PostProcessor:
         line = np.zeros((n, self.max_peaks), _PEAK_DT) if with_peaks else None
         rc = _lib.lib.ekp_results(self._ctx, num.ctypes.data, subset.ctypes.data, npk.ctypes.data,
                                   line.ctypes.data if with_peaks else None, ovf.ctypes.data)
-        _lib.check(rc)
+        if rc != _lib.ERR_CAPACITY or raise_on_overflow:   # the tables are written either way; `overflow` says what was cut
+            _lib.check(rc)
         out = dict(num_humans=num, subset=subset, n_peaks=npk, overflow=ovf)
         if with_peaks:
             po = np.zeros((n, 19), np.int32)
@@ -313,15 +315,66 @@ def paf_to_pose_cpp(heatmaps, pafs, config=None, *, frontend: str = "reference")
     return postprocess_batch(heat4, paf4, layout=layout, frontend=frontend, thr=config.TEST.THRESH_HEATMAP)[0]
 
 
+def compute_resized_coords(coords, resizeFactor):
+    """paf_to_pose.py:39-57: index of a cell after resizing its array by resizeFactor, (c + 0.5) * f - 0.5."""
+    return (np.array(coords, dtype=float) + 0.5) * resizeFactor - 0.5
+
+
+def _coarse_peaks(heat_hwc: np.ndarray, thr: float):
+    """Stride-8 maxima of every part map on the GPU: (line, part_off) of the part-sorted peak table, rows at
+    (8x + 3, 8y + 3) in (part, y, x) order."""
+    h, w, _ = heat_hwc.shape
+    pp = _processor(0, 1, h, w, 2048, 128)
+    while True:
+        pp.run(heat_hwc[None], np.zeros((1, h, w, _lib.PAF_CH), np.float32), layout="nhwc", frontend="reference_coarse", thr=thr)
+        # only the peak table matters here: more than EKP_MAX_PART peaks of one part (or whatever stages 4-5 ran
+        # into on an arbitrary map) does not cut it, more than max_peaks does
+        res = pp.results(with_peaks=True, raise_on_overflow=False)
+        if not int(res["overflow"][0]) & _lib.OVF_PEAKS:
+            return res["peaks"][0], res["part_off"][0]
+        if pp.max_peaks >= 16384:
+            raise _lib.EkpCapacityError(_lib.ERR_CAPACITY, "more than 16384 peaks in one image")
+        pp = _processor(0, 1, h, w, min(pp.max_peaks * 4, 16384), 128)
+
+
+def find_peaks(param, img):
+    """Drop-in for paf_to_pose.py:26-36: the local maxima (4-neighbour cross, in-bounds neighbours only) of a 2-D
+    map that exceed ``param``, as an int array of [x, y] rows in row-major order.  Runs on the GPU (the map
+    travels as part 0 of an otherwise empty heat tensor)."""
+    img = np.asarray(img, np.float32)
+    if img.ndim != 2:
+        raise ValueError("img must be 2-D")
+    h, w = img.shape
+    if h < 5 or w < 5:
+        raise ValueError("the CUDA path needs maps of at least 5 x 5")
+    heat = np.full((h, w, _lib.HEAT_CH), -np.inf, np.float32)
+    heat[:, :, 0] = img
+    line, po = _coarse_peaks(heat, float(param))
+    rows = line[po[0]:po[1]]
+    return np.stack([(rows["x"] - 3) // 8, (rows["y"] - 3) // 8], axis=1).astype(np.int64).reshape(-1, 2)
+
+
 def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False, config=None):
-    """Drop-in for paf_to_pose.py:60-133: list of 18 float64 arrays ``[n_k, 4]`` = (x, y, score, id)."""
+    """Drop-in for paf_to_pose.py:60-133: list of 18 float64 arrays ``[n_k, 4]`` = (x, y, score, id).
+    bool_refine_center=False returns the stride-8 maxima at compute_resized_coords(peak, 8) with the heat value
+    as score (:119-122)."""
     config = config or default_cfg
-    if not bool_refine_center or bool_gaussian_filt or int(upsampFactor) != 8:
-        raise NotImplementedError("only the configuration the reference's callers use is built: "
-                                  "upsampFactor=8, bool_refine_center=True, bool_gaussian_filt=False "
-                                  "(paf_to_pose.py:348)")
+    if bool_gaussian_filt or int(upsampFactor) != 8:
+        raise NotImplementedError("built: upsampFactor=8 (lib/config/default.py:17), bool_gaussian_filt=False (dead code "
+                                  "in the reference, paf_to_pose.py:111-112)")
     heatmaps = np.ascontiguousarray(heatmaps, np.float32)
     h, w, _ = heatmaps.shape
+    if not bool_refine_center:
+        line, po = _coarse_peaks(heatmaps, config.TEST.THRESH_HEATMAP)
+        out = []
+        for k in range(config.MODEL.NUM_KEYPOINTS):
+            rows = line[po[k]:po[k + 1]]
+            arr = np.zeros((len(rows), 4))
+            arr[:, 0] = compute_resized_coords((rows["x"] - 3) // 8, 8)
+            arr[:, 1] = compute_resized_coords((rows["y"] - 3) // 8, 8)
+            arr[:, 2], arr[:, 3] = rows["score"], rows["id"]
+            out.append(arr)
+        return out
     pp = _processor(0, 1, h, w, 2048, 128)
     pp.run(heatmaps[None], np.zeros((1, h, w, _lib.PAF_CH), np.float32), layout="nhwc", frontend="reference",
            thr=config.TEST.THRESH_HEATMAP)
