@@ -478,8 +478,8 @@ def test_argument_errors(ek, pp):
 
 @pytest.mark.parametrize("people", [20, 50, 100, 150])
 def test_assembly_paths_by_people_count(ek, people):
-    """20 / 50 / 100 / 150 four-part people in one image drive the assembly through its 32-, 64- and
-    128-row register paths and the shared-memory path; all must equal the oracle bit for bit."""
+    """20 / 50 / 100 / 150 four-part people in one image: one chunk of connections per limb and several (the
+    assembly takes one lane per connection, 32 at a time); all must equal the oracle bit for bit."""
     H, W = 32, 40 * people + 24
     paf = np.zeros((1, H, W, 38), np.float32)
     rows = []

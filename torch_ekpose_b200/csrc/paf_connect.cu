@@ -19,7 +19,7 @@
 //  * sorting (pafprocess.cpp:97): the reference's result depends on HOW std::sort permutes equal
 //    scores.  For n <= 16 libstdc++ runs a stable insertion sort, and without ties the order is
 //    unique, so all threads rank the candidates in parallel (stable) and look for ties; only when
-//    n > 16 AND ties exist does one thread replay libstdc++'s algorithm on the original sequence
+//    n > 16 AND ties exist does one warp replay libstdc++'s algorithm on the original sequence
 //    (introsort: median-of-3 quicksort above 16 elements, heapsort after 2*floor(log2 n) levels,
 //    then the final insertion sort), which reproduces the reference's permutation exactly.
 #include "common.cuh"
