@@ -14,7 +14,7 @@
 //    pair whose four MIDDLE samples (i = 3..6, the most discriminative ones: the ends lie on the true limbs
 //    of a and b) all fail can never pass.  Pass 1 evaluates only those four (same float operations as the
 //    full evaluation, so the test is exact) and keeps the survivors in pair order; pass 2 runs the full,
-//    unmodified evaluation on the survivors only.  In crowded scenes > 90 % of the pairs end in pass 1;
+//    unmodified evaluation on the survivors only.  In crowded scenes roughly 70 % of the pairs end in pass 1 (from the pass times);
 //    the gathers are what the kernel is bound by (fully divergent loads: one L1 tag per lane per load);
 //  * sorting (pafprocess.cpp:97): the reference's result depends on HOW std::sort permutes equal
 //    scores.  For n <= 16 libstdc++ runs a stable insertion sort, and without ties the order is
