@@ -437,6 +437,26 @@ def test_overflow_is_reported(ek):
     small.close()
 
 
+def test_inputs_that_are_only_4_byte_aligned(ek):
+    """Device inputs at an odd float offset (views into a bigger buffer): same people as the aligned tensors."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(3, 46, 54, (2, 4), seed=9)
+    pp_ = ek.PostProcessor(device=0, max_batch=3, max_h=46, max_w=54, max_peaks=1024, max_humans=32)
+    pp_.run(_dev(heat), _dev(paf), frontend="dense", materialize=True)
+    want = pp_.results()
+    hb = torch.zeros(heat.size + 3, dtype=torch.float32, device="cuda")
+    pb = torch.zeros(paf.size + 1, dtype=torch.float32, device="cuda")
+    hv, pv = hb[3:].view(heat.shape), pb[1:].view(paf.shape)
+    hv.copy_(torch.from_numpy(heat)); pv.copy_(torch.from_numpy(paf))
+    assert hv.data_ptr() % 16 != 0 and pv.data_ptr() % 16 != 0
+    for materialize in (True, False):
+        pp_.run(hv, pv, frontend="dense", materialize=materialize)
+        got = pp_.results()
+        assert np.array_equal(got["num_humans"], want["num_humans"])
+        assert_bits_equal(got["subset"], want["subset"], "subset")
+    pp_.close()
+
+
 def test_small_context_does_not_shrink_kernel_limits_of_a_big_one(ek):
     """Kernel attributes (dynamic shared memory limits) are per device, not per context: creating a context
     with small capacities after a big one must leave the big one working."""

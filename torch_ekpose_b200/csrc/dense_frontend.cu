@@ -2,8 +2,8 @@
 //
 // One launch takes the network's stride-8 heat (19 ch) and PAF (38 ch) maps of a whole batch
 // and, per 16-row x (8*tile_wl)-column full-resolution tile (one CTA),
-//   (0) first wave of CTAs only: prefetches the whole batch's inputs into L2 (evict_last) in one
-//       burst, so input reads do not trickle in between the writes (HBM read/write turnarounds),
+//   (0) first wave of CTAs only: prefetches the whole batch's inputs into L2 (evict_last, TMA bulk
+//       prefetch) in one burst, so input reads do not trickle in between the writes,
 //   (1) stages the stride-8 neighbourhood of the tile in shared memory (HWC order) with cp.async,
 //   (2) optionally materialises the bilinear x8 tensors heat_mat[H][W][19] / paf_mat[H][W][38]
 //       (the operator-surface tensors of process_paf, paf_to_pose.py:356-360) -- the HBM-bound part:
@@ -63,6 +63,7 @@ namespace ekp {
 #ifndef EKP_MAX_TWL
 #define EKP_MAX_TWL 32
 #endif
+
 constexpr int kMaxTwl = EKP_MAX_TWL;          // widest tile in stride-8 columns
 constexpr int kLeanThreads = EKP_LEAN_THREADS;  // CTA size / resident CTAs per SM without materialisation
 constexpr int kLeanBlocks = EKP_LEAN_BLOCKS;
@@ -618,7 +619,6 @@ __device__ __forceinline__ void process_tile_mat(const DenseParams& p, const Til
 template <bool kMat, bool kDebug>
 __global__ void __launch_bounds__(kMat ? kMatThreads : kLeanThreads, kMat ? kMatBlocks : kLeanBlocks)
 dense_frontend_kernel(const DenseParams p) {
-    constexpr int kThreads = kMat ? kMatThreads : kLeanThreads;
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) float sTaps[64];
     __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];
@@ -636,20 +636,31 @@ dense_frontend_kernel(const DenseParams p) {
     sm.store = reinterpret_cast<float4*>(smem + (((size_t) (ctl.colmax + hcols * EKP_HEAT_CH - smem) + 31) & ~(size_t) 31));
     const TileGeom g = tile_geom(p, blockIdx.x, blockIdx.y, blockIdx.z);
     if (!kDebug) {
-        // The first wave of CTAs pulls the WHOLE batch's stride-8 inputs into L2 (evict_last) in one
-        // burst before the write stream builds up.  Reads that trickle in between 2.3 GB of stores cost
-        // far more than their 36 MB (HBM read/write turnarounds): measured 0.415 -> 0.396 ms.
+        // The first wave of CTAs pulls the WHOLE batch's stride-8 inputs into L2 (evict_last) in one burst
+        // before the write stream builds up: reads that trickle in between 2.3 GB of stores cost far more than
+        // their 36 MB (HBM read/write turnarounds).  One thread per CTA hands its contiguous slice of each
+        // tensor to the TMA engine (cp.async.bulk.prefetch.L2); measured against per-line prefetch instructions
+        // by all threads (-1 %) and no prefetch (-2.3 %), profiles/README.md.
         const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         const unsigned ncta = gridDim.x * gridDim.y * gridDim.z;
         constexpr unsigned kPrefetchCtas = 148u * (kMat ? kMatBlocks : kLeanBlocks);  // one resident wave on a B200
         const unsigned nfirst = ncta < kPrefetchCtas ? ncta : kPrefetchCtas;
-        if (lin < nfirst) {
-            const size_t heat_lines = ((size_t) p.n * EKP_HEAT_CH * p.h * p.w * 4 + 127) / 128;
-            const size_t paf_lines = kMat ? ((size_t) p.n * EKP_PAF_CH * p.h * p.w * 4 + 127) / 128 : 0;
-            for (size_t l = (size_t) lin * kThreads + threadIdx.x; l < heat_lines + paf_lines; l += (size_t) nfirst * kThreads) {
-                const char* a = l < heat_lines ? (const char*) p.heat + l * 128 : (const char*) p.paf + (l - heat_lines) * 128;
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
-            }
+        if (lin < nfirst && threadIdx.x == 0) {
+            unsigned long long policy;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+            auto prefetch_slice = [&](const float* base, size_t bytes) {
+                // 16-byte aligned pieces of [base, base + bytes): a hint, so the few bytes around a misaligned end do not matter
+                const uintptr_t lo = (reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t) 15;
+                const uintptr_t hi = (reinterpret_cast<uintptr_t>(base) + bytes) & ~(uintptr_t) 15;
+                if (hi <= lo) return;
+                const size_t per = (((size_t) (hi - lo) + nfirst - 1) / nfirst + 15) & ~(size_t) 15;
+                const uintptr_t a0 = lo + (size_t) lin * per;
+                if (a0 >= hi) return;
+                const unsigned sz = (unsigned) (a0 + per < hi ? per : hi - a0);
+                asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(a0), "r"(sz), "l"(policy));
+            };
+            prefetch_slice(p.heat, (size_t) p.n * EKP_HEAT_CH * p.h * p.w * 4);
+            if (kMat) prefetch_slice(p.paf, (size_t) p.n * EKP_PAF_CH * p.h * p.w * 4);
         }
     }
     __syncthreads();  // sTaps and the task counters are initialised
