@@ -20,10 +20,22 @@
 
 constexpr int H = 368, W = 432, N = 64, TB = 2;
 
+// HINT=1 (nvcc -DHINT=1): L2 evict_first policy on the bulk stores
+#ifndef HINT
+#define HINT 0
+#endif
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+#if HINT
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"((unsigned) __cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"((unsigned) __cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int K>
