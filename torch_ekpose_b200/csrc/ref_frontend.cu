@@ -132,13 +132,19 @@ cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream) {
 }
 
 // ---- nearest x8 upsample (paf_to_pose.py:356-359), HWC output --------------------------------
-// One block per (image, stride-8 row): stage the row as HWC in shared memory, then write the 8
-// identical full-resolution rows with 16-byte streaming stores.
+// One block per (image, stride-8 row): stage the row as HWC in shared memory, expand it x8 along x into a
+// shared-memory row buffer (<= kUpChunk stride-8 columns at a time), and let the TMA engine write it to the 8
+// identical full-resolution rows (cp.async.bulk shared -> global, one copy of up to 58 KB per output row,
+// L2 evict_first like the dense front-end's stores).
+constexpr int kUpChunk = 48;
 template <int C>
 __global__ void __launch_bounds__(256) upsample_nearest_kernel(const float* __restrict__ lo, int layout, int h, int w,
                                                                float* __restrict__ out) {
-    extern __shared__ __align__(16) float sRow[];  // [w][C]
+    extern __shared__ __align__(128) float sUp[];  // [8 * cw * C] expanded chunk, then [w][C] staged row
     const int j = blockIdx.x, img = blockIdx.y;
+    const int cw_max = w < kUpChunk ? w : kUpChunk;
+    float* sOut = sUp;
+    float* sRow = sUp + (size_t) 8 * cw_max * C;
     if (layout == EKP_LAYOUT_NCHW) {
         for (int idx = threadIdx.x; idx < C * w; idx += 256) {
             const int c = idx / w, i = idx - c * w;
@@ -149,28 +155,52 @@ __global__ void __launch_bounds__(256) upsample_nearest_kernel(const float* __re
     }
     __syncthreads();
     const int W = 8 * w;
-    const int row_f4 = W * C / 4;
-    float* base = out + (((size_t) img * 8 * h + 8 * j) * W) * C;
-    for (int col = threadIdx.x; col < row_f4; col += 256) {
-        float e[4];
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    for (int i0 = 0; i0 < w; i0 += cw_max) {
+        const int cw = min(cw_max, w - i0);
+        const int n4 = 8 * cw * C / 4;
+        for (int col = threadIdx.x; col < n4; col += 256) {
+            float e[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int f = col * 4 + k;
-            const int x = f / C, c = f - x * C;
-            e[k] = sRow[(x >> 3) * C + c];
+            for (int k = 0; k < 4; k++) {
+                const int f = col * 4 + k;
+                const int x = f / C, c = f - x * C;
+                e[k] = sRow[(i0 + (x >> 3)) * C + c];
+            }
+            reinterpret_cast<float4*>(sOut)[col] = make_float4(e[0], e[1], e[2], e[3]);
         }
-        const float4 v = make_float4(e[0], e[1], e[2], e[3]);
-#pragma unroll
-        for (int r = 0; r < 8; r++) __stcs(reinterpret_cast<float4*>(base + (size_t) r * W * C) + col, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 8) {  // one output row each
+            float* dst = out + (((size_t) img * 8 * h + 8 * j + threadIdx.x) * W + 8 * i0) * C;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+                         "r"((unsigned) __cvta_generic_to_shared(sOut)), "r"((unsigned) (n4 * 16)), "l"(policy)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer is refilled (or the block exits) next
+        }
+        __syncthreads();
     }
 }
 
+static size_t upsample_smem(int w, int C) {
+    const int cw = w < kUpChunk ? w : kUpChunk;
+    return sizeof(float) * ((size_t) 8 * cw * C + (size_t) w * C);
+}
 cudaError_t launch_upsample_nearest(const float* lo, int layout, int n, int h, int w, int C, float* out, cudaStream_t stream) {
     dim3 grid(h, n);
-    const size_t smem = sizeof(float) * (size_t) w * C;
-    if (C == EKP_PAF_CH) upsample_nearest_kernel<EKP_PAF_CH><<<grid, 256, smem, stream>>>(lo, layout, h, w, out);
-    else if (C == EKP_HEAT_CH) upsample_nearest_kernel<EKP_HEAT_CH><<<grid, 256, smem, stream>>>(lo, layout, h, w, out);
-    else return cudaErrorInvalidValue;
+    const size_t smem = upsample_smem(w, C);
+    cudaError_t e;
+    if (C == EKP_PAF_CH) {
+        e = raise_dynamic_smem_limit(upsample_nearest_kernel<EKP_PAF_CH>, smem);
+        if (e != cudaSuccess) return e;
+        upsample_nearest_kernel<EKP_PAF_CH><<<grid, 256, smem, stream>>>(lo, layout, h, w, out);
+    } else if (C == EKP_HEAT_CH) {
+        e = raise_dynamic_smem_limit(upsample_nearest_kernel<EKP_HEAT_CH>, smem);
+        if (e != cudaSuccess) return e;
+        upsample_nearest_kernel<EKP_HEAT_CH><<<grid, 256, smem, stream>>>(lo, layout, h, w, out);
+    } else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
