@@ -319,6 +319,7 @@ extern "C" int ekp_debug_conn_profile(unsigned long long* out16, int reset) {
 // Ordered compaction step shared by both passes: every thread of the block contributes `flag`; returns the
 // number of flagged threads before this one plus `base`, and advances `base` by the block's total (identical
 // in every thread).  Two block barriers.
+template <int kT>
 __device__ __forceinline__ int ordered_slot(bool flag, int* sWarpCnt, int& base) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned mask = __ballot_sync(0xffffffffu, flag);
@@ -326,7 +327,7 @@ __device__ __forceinline__ int ordered_slot(bool flag, int* sWarpCnt, int& base)
     __syncthreads();
     int before = 0, all = 0;
 #pragma unroll
-    for (int k = 0; k < kConnThreads / 32; k++) {
+    for (int k = 0; k < kT / 32; k++) {
         const int c = sWarpCnt[k];
         if (k < warp) before += c;
         all += c;
@@ -337,8 +338,8 @@ __device__ __forceinline__ int ordered_slot(bool flag, int* sWarpCnt, int& base)
     return pos;
 }
 
-template <bool kVec2>
-__global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_peak* __restrict__ line,
+template <bool kVec2, int kT>
+__global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restrict__ line,
                                                                    const int* __restrict__ part_off, int max_peaks,
                                                                    const PafSource paf, int h1, Conn* __restrict__ conns,
                                                                    int* __restrict__ n_conns,
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     __shared__ float sScore2[EKP_MAX_CAND];
     __shared__ unsigned sTag2[EKP_MAX_CAND];   // pass-1 survivors while scoring, then the ranked tags
     __shared__ int sTies;
-    __shared__ int sWarpCnt[kConnThreads / 32];
+    __shared__ int sWarpCnt[kT / 32];
     __shared__ unsigned sUsedA[EKP_MAX_PART / 32], sUsedB[EKP_MAX_PART / 32];
     static_assert(kSurvWindow <= EKP_MAX_CAND, "the survivor list lives in sTag2");
     const int limb = blockIdx.x, img = blockIdx.y;
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     unsigned long long prof_t = prof_now();
 #endif
     const ekp_peak* L = line + (size_t) img * max_peaks;
-    for (int i = threadIdx.x; i < nA; i += kConnThreads) sA[i] = L[offA + i];
-    for (int i = threadIdx.x; i < nB; i += kConnThreads) sB[i] = L[offB + i];
+    for (int i = threadIdx.x; i < nA; i += kT) sA[i] = L[offA + i];
+    for (int i = threadIdx.x; i < nB; i += kT) sB[i] = L[offB + i];
     if (threadIdx.x < EKP_MAX_PART / 32) sUsedA[threadIdx.x] = sUsedB[threadIdx.x] = 0u;
     __syncthreads();
 
@@ -385,27 +386,27 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
     }
     int total = 0;  // candidates so far, identical in every thread
     // Few pairs (every scene but a crowd): one pass, one round trip to memory.  Otherwise pass 1 thins them out.
-    const bool two_pass = npairs > 2 * kConnThreads;
+    const bool two_pass = npairs > 2 * kT;
     for (int win = 0; win < npairs; win += kSurvWindow) {
         const int win_end = min(win + kSurvWindow, npairs);
         int nsurv = 0;  // pass 1: pairs of this window that can still pass, in pair order
         if (!two_pass) {
             nsurv = win_end - win;
-            for (int k = threadIdx.x; k < nsurv; k += kConnThreads) sTag2[k] = (unsigned) (win + k);
+            for (int k = threadIdx.x; k < nsurv; k += kT) sTag2[k] = (unsigned) (win + k);
         }
-        for (int base = win; two_pass && base < win_end; base += kConnThreads) {
+        for (int base = win; two_pass && base < win_end; base += kT) {
             const int pidx = base + threadIdx.x;
             bool keep = false;
             if (pidx < win_end) {
                 const int ia = pidx / nB;
                 keep = pair_may_pass<kVec2>(sA[ia], sB[pidx - ia * nB], paf, img, ch1, ch2, (packed_base + pidx) * 10);
             }
-            const int pos = ordered_slot(keep, sWarpCnt, nsurv);
+            const int pos = ordered_slot<kT>(keep, sWarpCnt, nsurv);
             if (keep) sTag2[pos] = (unsigned) pidx;
         }
         __syncthreads();
         PROF_MARK(1);  // pass 1
-        for (int base = 0; base < nsurv; base += kConnThreads) {  // pass 2: the full evaluation of the survivors
+        for (int base = 0; base < nsurv; base += kT) {  // pass 2: the full evaluation of the survivors
             const int k = base + threadIdx.x;
             bool pass = false;
             float crit = 0.f;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
                 ib = pidx - ia * nB;
                 pass = score_pair<kVec2>(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit, (packed_base + pidx) * 10);
             }
-            const int pos = ordered_slot(pass, sWarpCnt, total);
+            const int pos = ordered_slot<kT>(pass, sWarpCnt, total);
             if (pass && pos < EKP_MAX_CAND) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
         }
         __syncthreads();  // the survivor list is rewritten by the next window
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(kConnThreads) paf_connect_kernel(const ekp_pea
         if (total > EKP_MAX_CAND) atomicOr(overflow + img, EKP_OVF_CANDIDATES);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kConnThreads) {
+    for (int i = threadIdx.x; i < n; i += kT) {
         const float s = sScore[i];
         int rank = 0;
         bool tie = false;
@@ -562,8 +563,16 @@ cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int ma
     // both PAF channels of a limb with one 8-byte load: channel-last tensor, even channel count, aligned base
     const bool channel_last = paf.mode != PAF_PACKED && (paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC);
     const bool vec2 = channel_last && paf.C % 2 == 0 && reinterpret_cast<uintptr_t>(paf.ptr) % 8 == 0;
-    if (vec2) paf_connect_kernel<true><<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);
-    else paf_connect_kernel<false><<<grid, kConnThreads, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow);
+    // Blocks are latency-bound chains; a batch whose 19 x n blocks all fit on the GPU at once (crowded scenes come in
+    // small batches) gets twice the threads per block, bigger batches keep more blocks resident instead.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool wide = EKP_NUM_LIMB * n <= 4 * sms;
+#define EKP_LAUNCH_CONNECT(V, T) paf_connect_kernel<V, T><<<grid, T, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow)
+    if (vec2) { if (wide) EKP_LAUNCH_CONNECT(true, 2 * kConnThreads); else EKP_LAUNCH_CONNECT(true, kConnThreads); }
+    else { if (wide) EKP_LAUNCH_CONNECT(false, 2 * kConnThreads); else EKP_LAUNCH_CONNECT(false, kConnThreads); }
+#undef EKP_LAUNCH_CONNECT
     return cudaGetLastError();
 }
 
