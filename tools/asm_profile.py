@@ -17,7 +17,8 @@ def run(label, n, h, w, people, frontend, materialize):
     pp.run(hd, pd, frontend=frontend, materialize=materialize); pp.results()
     lib.ekp_debug_asm_profile(buf, 1)
     print(f"{label}: per image: staging {buf[0]/n/1e3:.2f} us, limbs tried in parallel {buf[1]/n/1e3:.2f} us, sequential limbs {buf[2]/n/1e3:.2f} us, "
-          f"prune+record {buf[3]/n/1e3:.2f} us; limbs parallel {buf[4]/n:.1f} sequential {buf[5]/n:.1f}")
+          f"prune+record {buf[3]/n/1e3:.2f} us; limbs parallel {buf[4]/n:.1f} sequential {buf[5]/n:.1f}; "
+          f"slowest image {buf[6]/1e3:.1f} us, most sequential limbs in one image {buf[7]}")
     pp.close()
 run("C4 crowded dense lean", 16, 92, 164, (30, 40), "dense", False)
 run("C4 crowded reference lean", 16, 92, 164, (30, 40), "reference", False)

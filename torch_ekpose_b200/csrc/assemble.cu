@@ -52,6 +52,75 @@ struct AsmInput {
     }
 };
 
+// (forward: argument for the parallel application is given at limb_parallel below)
+// K connections per lane (k = lane + 32 q), everything in registers: the usual case.
+template <int K>
+__device__ __forceinline__ bool limb_parallel_regs(const AsmInput& in, int limb, int max_humans, float* __restrict__ rows,
+                                                   int& nrows_io, bool& ovf, int* __restrict__ sClaim) {
+    const int lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
+    const int nc = in.sStart[limb + 1] - in.sStart[limb];
+    const int nrows = nrows_io;
+    ConnRec cn[K];
+    int found[K], s1[K];
+    bool active[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        active[q] = lane + 32 * q < nc;
+        found[q] = 0; s1[q] = -1;
+        if (active[q]) cn[q] = in.rec_at(limb, lane + 32 * q);
+    }
+    for (int r = 0; r < nrows; r++) {  // every lane reads the same two words: broadcast
+        const float a = rows[r * 20 + p1], b = rows[r * 20 + p2];
+#pragma unroll
+        for (int q = 0; q < K; q++)
+            if (active[q] && (a == cn[q].f1 || b == cn[q].f2)) { found[q]++; s1[q] = r; }
+    }
+    bool bad = false;
+    if (K == 1) {  // a row matched by two connections shows up as two lanes with the same s1
+        const unsigned peers = __match_any_sync(FULL, s1[0] >= 0 ? s1[0] : -1 - lane);
+        bad = found[0] >= 2 || (s1[0] >= 0 && (peers & (peers - 1)) != 0u);
+    } else {       // ... or as a claim that does not read back
+#pragma unroll
+        for (int q = 0; q < K; q++)
+            if (s1[q] >= 0) sClaim[s1[q]] = lane + 32 * q;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < K; q++) bad |= found[q] >= 2 || (s1[q] >= 0 && sClaim[s1[q]] != lane + 32 * q);
+    }
+    if (__any_sync(FULL, bad)) return false;
+    int nnew = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        if (s1[q] >= 0) {  // found == 1, pafprocess.cpp:146-151
+            if (rows[s1[q] * 20 + p2] != cn[q].f2) {
+                rows[s1[q] * 20 + p2] = cn[q].f2;
+                rows[s1[q] * 20 + 19] = __fadd_rn(rows[s1[q] * 20 + 19], 1.0f);
+                rows[s1[q] * 20 + 18] = __fadd_rn(rows[s1[q] * 20 + 18], cn[q].s_ext);
+            }
+        }
+        const bool starts = active[q] && s1[q] < 0 && limb < 18;  // found == 0, :173-183
+        const unsigned mask = __ballot_sync(FULL, starts);
+        if (starts) {
+            const int r = nrows + nnew + __popc(mask & ((1u << lane) - 1u));
+            if (r < max_humans) {
+#pragma unroll
+                for (int c = 0; c < 18; c++) rows[r * 20 + c] = -1.0f;
+                rows[r * 20 + p1] = cn[q].f1;
+                rows[r * 20 + p2] = cn[q].f2;
+                rows[r * 20 + 18] = cn[q].s_new;
+                rows[r * 20 + 19] = 2.0f;
+            }
+        }
+        nnew += __popc(mask);
+    }
+    if (nrows + nnew > max_humans) { ovf = true; nnew = max_humans - nrows; }
+    nrows_io = nrows + nnew;
+    __syncwarp();
+    return true;
+}
+
 // ---- one limb, all connections at once -------------------------------------------------------------
 // Let the limb's connections be k = 0..nc-1 (acceptance order), with distinct f1 (cid1) and distinct f2
 // (cid2).  Against the rows at the START of the limb, connection k matches found_k rows.  Claim: if every
@@ -70,46 +139,8 @@ __device__ bool limb_parallel(const AsmInput& in, int limb, int max_humans, floa
     const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
     const int nc = in.sStart[limb + 1] - in.sStart[limb];
     const int nrows = nrows_io;
-    if (nc <= 32) {  // the usual case: one connection per lane, everything in registers
-        const bool active = lane < nc;
-        ConnRec cn;
-        int found = 0, s1 = -1;
-        if (active) {
-            cn = in.rec_at(limb, lane);
-            for (int r = 0; r < nrows; r++) {  // every lane reads the same two words: broadcast
-                const bool m = rows[r * 20 + p1] == cn.f1 || rows[r * 20 + p2] == cn.f2;
-                if (m) { found++; s1 = r; }
-            }
-        }
-        // a row matched by two connections shows up as two lanes with the same s1
-        const unsigned peers = __match_any_sync(FULL, s1 >= 0 ? s1 : -1 - lane);
-        if (__any_sync(FULL, found >= 2 || (s1 >= 0 && (peers & (peers - 1)) != 0u))) return false;
-        if (s1 >= 0) {  // found == 1, pafprocess.cpp:146-151
-            if (rows[s1 * 20 + p2] != cn.f2) {
-                rows[s1 * 20 + p2] = cn.f2;
-                rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
-            }
-        }
-        const bool starts = active && s1 < 0 && limb < 18;  // found == 0, :173-183
-        const unsigned mask = __ballot_sync(FULL, starts);
-        if (starts) {
-            const int r = nrows + __popc(mask & ((1u << lane) - 1u));
-            if (r < max_humans) {
-#pragma unroll
-                for (int q = 0; q < 18; q++) rows[r * 20 + q] = -1.0f;
-                rows[r * 20 + p1] = cn.f1;
-                rows[r * 20 + p2] = cn.f2;
-                rows[r * 20 + 18] = cn.s_new;
-                rows[r * 20 + 19] = 2.0f;
-            }
-        }
-        int nnew = __popc(mask);
-        if (nrows + nnew > max_humans) { ovf = true; nnew = max_humans - nrows; }
-        nrows_io = nrows + nnew;
-        __syncwarp();
-        return true;
-    }
+    if (nc <= 32) return limb_parallel_regs<1>(in, limb, max_humans, rows, nrows_io, ovf, sClaim);
+    if (nc <= 64) return limb_parallel_regs<2>(in, limb, max_humans, rows, nrows_io, ovf, sClaim);
     // search: matched row (or -1: none) per connection; two or more matches end the attempt
     bool bad = false;
     for (int k0 = 0; k0 < nc; k0 += 32) {
@@ -172,21 +203,54 @@ __device__ bool limb_parallel(const AsmInput& in, int limb, int max_humans, floa
     return true;
 }
 
-// ---- one limb, connection by connection (the reference's walk; the row search is spread over the lanes) ----
+// ---- one limb, connection by connection (the reference's walk) ---------------------------------------
+// The row search is spread over the lanes; for up to 128 rows the two columns it compares (p1, p2) live in
+// registers (row r in lane r & 31, slot r >> 5) and are kept in step with the rows in shared memory, so a step
+// costs ballots instead of shared-memory round trips.
+constexpr int kSeqSlots = 4;
 __device__ void limb_sequential(const AsmInput& in, int limb, int max_humans, float* __restrict__ rows, int& nrows_io, bool& ovf) {
     const int lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
     int nrows = nrows_io;
-    {
-        const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
-        const int nc = in.sStart[limb + 1] - in.sStart[limb];
-        for (int k = 0; k < nc; k++) {
-            const ConnRec cn = in.rec_at(limb, k);
-            const float f1 = cn.f1, f2 = cn.f2;
-            int found = 0, s1 = 0, s2 = 0;
+    const int p1 = kPairs[limb][0], p2 = kPairs[limb][1];
+    const int nc = in.sStart[limb + 1] - in.sStart[limb];
+    const bool cached = max_humans <= 32 * kSeqSlots;
+    float c1[kSeqSlots], c2[kSeqSlots];
+    auto reload = [&]() {
+#pragma unroll
+        for (int s = 0; s < kSeqSlots; s++) {
+            const int r = 32 * s + lane;
+            c1[s] = r < nrows ? rows[r * 20 + p1] : -1.0f;
+            c2[s] = r < nrows ? rows[r * 20 + p2] : -1.0f;
+        }
+    };
+    if (cached) reload();
+    for (int k = 0; k < nc; k++) {
+        const ConnRec cn = in.rec_at(limb, k);
+        const float f1 = cn.f1, f2 = cn.f2;
+        int found = 0, s1 = 0, s2 = 0;
+        if (cached) {
+#pragma unroll
+            for (int s = 0; s < kSeqSlots; s++) {
+                if (32 * s >= nrows) break;
+                unsigned mask = __ballot_sync(FULL, 32 * s + lane < nrows && (c1[s] == f1 || c2[s] == f2));
+                const int c = __popc(mask);
+                if (c) {
+                    if (found == 0) {
+                        s1 = 32 * s + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (mask) s2 = 32 * s + __ffs(mask) - 1;
+                    } else if (found == 1) {
+                        s2 = 32 * s + __ffs(mask) - 1;
+                    }
+                    found += c;
+                }
+            }
+        } else {
             for (int base = 0; base < nrows; base += 32) {
                 const int r = base + lane;
                 const bool m = r < nrows && (rows[r * 20 + p1] == f1 || rows[r * 20 + p2] == f2);
-                unsigned mask = __ballot_sync(0xffffffffu, m);
+                unsigned mask = __ballot_sync(FULL, m);
                 const int c = __popc(mask);
                 if (c) {
                     if (found == 0) {
@@ -199,48 +263,63 @@ __device__ void limb_sequential(const AsmInput& in, int limb, int max_humans, fl
                     found += c;
                 }
             }
-            if (found == 1) {
-                if (lane == 0 && rows[s1 * 20 + p2] != f2) {
-                    rows[s1 * 20 + p2] = f2;
-                    rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
-                }
-            } else if (found == 2) {
-                const bool both = lane < 18 && rows[s1 * 20 + lane] > 0.f && rows[s2 * 20 + lane] > 0.f;
-                const bool membership = __any_sync(0xffffffffu, both);
-                if (!membership) {
-                    if (lane < 18) rows[s1 * 20 + lane] = __fadd_rn(rows[s1 * 20 + lane], __fadd_rn(rows[s2 * 20 + lane], 1.0f));
-                    if (lane == 19) rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], rows[s2 * 20 + 19]);
-                    if (lane == 18) {
-                        const float v = __fadd_rn(rows[s1 * 20 + 18], rows[s2 * 20 + 18]);
-                        rows[s1 * 20 + 18] = __fadd_rn(v, cn.score);
-                    }
-                    __syncwarp();
-                    if (lane < 20)  // erase row s2: every lane shifts its own column
-                        for (int r = s2; r < nrows - 1; r++) rows[r * 20 + lane] = rows[(r + 1) * 20 + lane];
-                    nrows--;
-                } else if (lane == 0) {
-                    rows[s1 * 20 + p2] = f2;
-                    rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
-                    rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
-                }
-            } else if (found == 0 && limb < 18) {
-                if (nrows < max_humans) {
-                    if (lane < 20) {
-                        float v = -1.0f;
-                        if (lane == p1) v = f1;
-                        if (lane == p2) v = f2;
-                        if (lane == 19) v = 2.0f;
-                        if (lane == 18) v = cn.s_new;
-                        rows[nrows * 20 + lane] = v;
-                    }
-                    nrows++;
-                } else {
-                    ovf = true;
-                }
-            }
-            __syncwarp();
         }
+        auto extend_s1 = [&]() {  // rows[s1][p2] = cid2, count + 1, score + (peak(cid2) + conn)
+            if (lane == 0) {
+                rows[s1 * 20 + p2] = f2;
+                rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], 1.0f);
+                rows[s1 * 20 + 18] = __fadd_rn(rows[s1 * 20 + 18], cn.s_ext);
+            }
+            if (cached && lane == (s1 & 31)) {
+#pragma unroll
+                for (int s = 0; s < kSeqSlots; s++)
+                    if (s == (s1 >> 5)) c2[s] = f2;
+            }
+        };
+        if (found == 1) {
+            // rows[s1][p2] != cid2, read from the cache's owner or from shared memory
+            const bool differs = rows[s1 * 20 + p2] != f2;
+            if (differs) extend_s1();
+        } else if (found == 2) {
+            const bool both = lane < 18 && rows[s1 * 20 + lane] > 0.f && rows[s2 * 20 + lane] > 0.f;
+            const bool membership = __any_sync(FULL, both);
+            if (!membership) {
+                if (lane < 18) rows[s1 * 20 + lane] = __fadd_rn(rows[s1 * 20 + lane], __fadd_rn(rows[s2 * 20 + lane], 1.0f));
+                if (lane == 19) rows[s1 * 20 + 19] = __fadd_rn(rows[s1 * 20 + 19], rows[s2 * 20 + 19]);
+                if (lane == 18) {
+                    const float v = __fadd_rn(rows[s1 * 20 + 18], rows[s2 * 20 + 18]);
+                    rows[s1 * 20 + 18] = __fadd_rn(v, cn.score);
+                }
+                __syncwarp();
+                if (lane < 20)  // erase row s2: every lane shifts its own column
+                    for (int r = s2; r < nrows - 1; r++) rows[r * 20 + lane] = rows[(r + 1) * 20 + lane];
+                nrows--;
+                __syncwarp();
+                if (cached) reload();  // rare: rows moved
+            } else {
+                extend_s1();
+            }
+        } else if (found == 0 && limb < 18) {
+            if (nrows < max_humans) {
+                if (lane < 20) {
+                    float v = -1.0f;
+                    if (lane == p1) v = f1;
+                    if (lane == p2) v = f2;
+                    if (lane == 19) v = 2.0f;
+                    if (lane == 18) v = cn.s_new;
+                    rows[nrows * 20 + lane] = v;
+                }
+                if (cached && lane == (nrows & 31)) {
+#pragma unroll
+                    for (int s = 0; s < kSeqSlots; s++)
+                        if (s == (nrows >> 5)) { c1[s] = f1; c2[s] = f2; }
+                }
+                nrows++;
+            } else {
+                ovf = true;
+            }
+        }
+        __syncwarp();
     }
     nrows_io = nrows;
 }
@@ -249,7 +328,7 @@ __device__ void limb_sequential(const AsmInput& in, int limb, int max_humans, fl
 __device__ unsigned long long g_asm_prof[8];
 __device__ __forceinline__ unsigned long long asm_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define APROF(k) do { if (threadIdx.x == 0) { const unsigned long long _t = asm_now(); atomicAdd(&g_asm_prof[k], _t - prof_t); prof_t = _t; } } while (0)
-#define ACOUNT(k) do { if (threadIdx.x == 0) atomicAdd(&g_asm_prof[k], 1ull); } while (0)
+#define ACOUNT(k) do { if (threadIdx.x == 0) { atomicAdd(&g_asm_prof[k], 1ull); if (k == 5) prof_nseq++; } } while (0)
 extern "C" int ekp_debug_asm_profile(unsigned long long* out8, int reset) {
     cudaMemcpyFromSymbol(out8, g_asm_prof, sizeof(unsigned long long) * 8);
     if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_asm_prof, z, sizeof(z)); }
@@ -275,6 +354,8 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     const int img = blockIdx.x, lane = threadIdx.x;
 #ifdef EKP_ASM_PROFILE
     unsigned long long prof_t = asm_now();
+    const unsigned long long prof_t0 = prof_t;
+    unsigned long long prof_nseq = 0;
 #endif
     const ekp_peak* L = line + (size_t) img * max_peaks;
     const Conn* Cimg = conns + (size_t) img * EKP_NUM_LIMB * EKP_MAX_PART;
@@ -297,11 +378,16 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
     if (staged) {
         // one flat pass so that all loads are in flight together (a per-limb loop would pay one
         // global-memory round trip per limb)
-        for (int idx = lane; idx < total_conns; idx += 32) {
-            int limb = 0;
+        int start[EKP_NUM_LIMB];  // per-limb offsets in registers: the limb of a flat index costs no memory access
 #pragma unroll
-            for (int l = 1; l < EKP_NUM_LIMB; l++) limb += (idx >= sStart[l]);
-            sRec[idx] = make_rec(Cimg[(size_t) limb * EKP_MAX_PART + (idx - sStart[limb])]);
+        for (int l = 0; l < EKP_NUM_LIMB; l++) start[l] = sStart[l];
+#pragma unroll 4
+        for (int idx = lane; idx < total_conns; idx += 32) {
+            int limb = 0, base = 0;
+#pragma unroll
+            for (int l = 1; l < EKP_NUM_LIMB; l++)
+                if (idx >= start[l]) { limb = l; base = start[l]; }
+            sRec[idx] = make_rec(Cimg[(size_t) limb * EKP_MAX_PART + (idx - base)]);
         }
     }
     __syncwarp();
@@ -360,6 +446,9 @@ __global__ void __launch_bounds__(32) assemble_kernel(const ekp_peak* __restrict
         hs[k] = __fdiv_rn(rows[r * 20 + 18], rows[r * 20 + 19]);  // get_score
     }
     APROF(3);  // prune + record
+#ifdef EKP_ASM_PROFILE
+    if (threadIdx.x == 0) { atomicMax(&g_asm_prof[6], asm_now() - prof_t0); atomicMax(&g_asm_prof[7], prof_nseq); }
+#endif
     if (lane == 0) {
         int4 head;
         head.x = kept;
