@@ -241,6 +241,33 @@ __device__ int warp_partition(const CandArray& A, int lo, int hi, float pivot, i
 }
 
 // `blocks`: scratch for one packed (first << 16 | last) entry per final range, >= n entries (n <= 65535).
+// The same partition, 32 swaps at a time, while the two scan fronts are at least 64 elements apart.  The sequential
+// loop alternates "advance lo over elements > pivot", "advance hi over elements < pivot", swap, ++lo: inside a window
+// of 32 elements per side the k-th element that stops the left scan is therefore swapped with the k-th element that
+// stops the right scan, and no position is examined again after its swap.  So the stoppers of both windows are found
+// with two ballots on the original values, the first min(nl, nr) pairs are swapped by one lane each, and the fronts
+// move exactly where the sequential scan would stand: past a window whose stoppers are used up, or ON the first unused
+// stopper of the other (it waits for a partner from the next window).  Returns with hi - lo < 64; the caller finishes
+// with warp_partition.
+__device__ void warp_partition_wide(const CandArray& A, int& lo, int& hi, float pivot) {
+    const int lane = threadIdx.x & 31;
+    while (hi - lo >= 64) {
+        const unsigned stopL = __ballot_sync(0xffffffffu, !(A.s[lo + lane] > pivot));       // comp(first, pivot) fails
+        const unsigned stopR = __ballot_sync(0xffffffffu, !(pivot > A.s[hi - 32 + lane]));  // comp(pivot, last) fails
+        const int nl = __popc(stopL), nr = __popc(stopR);
+        const int pairs = min(nl, nr);
+        if (lane < pairs) {
+            const int i = lo + (int) __fns(stopL, 0, lane + 1);           // lane-th stopper from the left
+            const int j = hi - 32 + (int) __fns(stopR, 31, -(lane + 1));  // lane-th stopper from the right
+            A.swap(i, j);
+        }
+        __syncwarp();
+        const int lo0 = lo, hi0 = hi;
+        lo = nl > pairs ? lo0 + (int) __fns(stopL, 0, pairs + 1) : lo0 + 32;
+        hi = nr > pairs ? hi0 - 32 + (int) __fns(stopR, 31, -(pairs + 1)) + 1 : hi0 - 32;
+    }
+}
+
 __device__ void std_sort_desc(const CandArray& A, int n, unsigned* blocks) {
     if (n <= 0) return;
     const int lane = threadIdx.x & 31;
@@ -275,7 +302,10 @@ __device__ void std_sort_desc(const CandArray& A, int n, unsigned* blocks) {
                 else A.swap(first, b);
             }
             __syncwarp();
-            const int cut = warp_partition(A, first + 1, last, A.s[first], n);
+            int plo = first + 1, phi = last;
+            const float pivot = A.s[first];
+            warp_partition_wide(A, plo, phi, pivot);
+            const int cut = warp_partition(A, plo, phi, pivot, n);
             stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
             last = cut;
         }
