@@ -396,7 +396,7 @@ def run_ours(args, rank, local_rank, world):
         peak, peak_src = measured_peak()
         images = BATCH * world * args.steps
         value = images / (ms / 1000.0)
-        # Roofline of the dominant kernel (fused stages 1-3).  The steps are pipelined over two streams,
+        # Roofline of the dominant kernel (fused stages 1-3).  The steps are pipelined over N_CTX streams,
         # so per-kernel event intervals overlap each other; the honest per-launch duration over the
         # timed region is (timed region) / (launches) = ms_per_step, which also charges the kernel for
         # everything else in the step (a lower bound on its bandwidth).  kernel_ms_isolated is the same
