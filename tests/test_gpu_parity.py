@@ -422,6 +422,17 @@ def test_stage45_adversarial_fuzz_vs_oracle(ek, seed):
         assert m == len(sub), f"case {i}: {m} people vs {len(sub)}"
         assert_bits_equal(res["subset"][i, :m], sub, f"case {i}")
     big.close()
+    # the same scenes through a context with few rows (<= 128): the sequential walk then keeps the two compared
+    # columns in registers, merges included
+    few = [i for i in range(n) if len(cases[i][0]) < 400]
+    small = ek.PostProcessor(device=0, max_batch=len(few), max_h=16, max_w=24, max_peaks=1024, max_humans=128)
+    small.run_peaks(_dev(peaks[few]), _dev(counts[few]), _dev(paf[few]), h1=H)
+    res2 = small.results()
+    for j, i in enumerate(few):
+        m = int(res["num_humans"][i])
+        assert int(res2["num_humans"][j]) == m
+        assert_bits_equal(res2["subset"][j, :m], res["subset"][i, :m], f"case {i}, 128-row context")
+    small.close()
 
 
 # ---------------------------------------------------------------------------------------------
