@@ -93,6 +93,8 @@ const char *ekp_version(void);
  *       (paf_to_pose.py:356-360).  DENSE front-end: bilinear x8 (paf_mat is then also what
  *       stage 4 samples); REFERENCE front-end: nearest x8.  Pass NULL to skip materialising;
  *       stage 4 then computes the identical sample values from the stride-8 PAF.
+ *       Both must be 16-byte aligned (they are written by the TMA engine in 16-byte units); heat / paf need
+ *       only their natural 4-byte alignment.
  * Replaces paf_to_pose_cpp lines 346-360 (NMS + upsample + process_paf) for a whole batch. */
 int ekp_postprocess(ekp_ctx *ctx, const float *heat, const float *paf, int n, int h, int w, int layout,
                     float thr_heat, int frontend, float *heat_mat, float *paf_mat, void *stream);
