@@ -322,6 +322,7 @@ extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, 
     CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
     PafSource src;
     src.layout = layout; src.H = 8 * h; src.W = 8 * w; src.C = EKP_PAF_CH; src.h = h; src.w = w;
+    src.pair_base = nullptr; src.ids_are_rows = 1;
     if (frontend == EKP_FRONTEND_DENSE) {
         rc = ensure_tables(c, h, w, st);
         if (rc) return rc;
@@ -397,6 +398,7 @@ extern "C" int ekp_process_paf_dev(ekp_ctx* c, const float* peaks, const int* n_
     c->launches += 1;
     PafSource src;
     src.ptr = paf_mat; src.mode = PAF_FULL_HWC; src.layout = EKP_LAYOUT_NHWC; src.H = H; src.W = W; src.C = C; src.h = H / 8; src.w = W / 8;
+    src.pair_base = nullptr; src.ids_are_rows = 0;
     return run_back_half(c, n, /*id_from_key=*/1, src, h1, st);
 }
 
@@ -671,6 +673,7 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
         c->launches += 1;
         PafSource src;
         src.layout = EKP_LAYOUT_NHWC; src.H = f1; src.W = f2; src.C = f3; src.h = f1 / 8; src.w = f2 / 8; src.pair_base = nullptr;
+        src.ids_are_rows = 0;
         rc = run_peak_sort(c, 1, /*id_from_key=*/1, st);
         if (rc) return rc;
         if (sparse && nsamples > 0) {

@@ -44,6 +44,8 @@ struct PafSource {
     int H, W, C;       // full-resolution dims and channel count
     int h, w;          // stride-8 dims (modes 1, 2)
     const int* pair_base;  // [20] prefix of nA*nB over the limbs (mode 3)
+    int ids_are_rows;      // 1: a peak's id IS its row in the part-sorted table (front-end paths), so the score the
+                           // reference looks up as peak_infos_line[cid] is the peak's own; 0: process_paf input order
 };
 
 // pafprocess.h:16-24

@@ -511,7 +511,10 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
             if (lane == leader) {
                 Conn cn;
                 cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c];
-                cn.s_ext = cn.s_new = 0.f; cn.pad0 = cn.pad1 = cn.pad2 = 0;
+                const float ps1 = sA[i1].score, ps2 = sB[i2].score;  // == peak_infos_line[cid].score when ids are rows
+                cn.s_ext = __fadd_rn(ps2, cn.score);
+                cn.s_new = __fadd_rn(__fadd_rn(ps1, ps2), cn.score);
+                cn.pad0 = cn.pad1 = cn.pad2 = 0;
                 out[nc] = cn;
                 sUsedA[i1 >> 5] |= 1u << (i1 & 31);
                 sUsedB[i2 >> 5] |= 1u << (i2 & 31);
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
     // the score sums the assembly needs per connection, here where 19 x n warps can fetch the peak scores in
     // parallel (one warp per image would pay the two dependent round trips alone)
     __syncwarp();
-    for (int k = lane; k < min(nc, EKP_MAX_PART); k += 32) {
+    for (int k = lane; !paf.ids_are_rows && k < min(nc, EKP_MAX_PART); k += 32) {  // process_paf input: ids index the table
         const float sc = out[k].score;
         const float p1 = L[out[k].cid1].score, p2 = L[out[k].cid2].score;
         out[k].s_ext = __fadd_rn(p2, sc);
