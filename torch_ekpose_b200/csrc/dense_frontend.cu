@@ -85,10 +85,13 @@ static_assert(kFillWarps >= 1 && kNmsThreads >= 32 && kNmsThreads % 32 == 0 && k
 enum { BAR_FILL = 1, BAR_NMS = 2, BAR_HEAT_READY = 3 };  // named barriers (0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-constexpr int kTH = 16;             // full-resolution rows per tile
-constexpr int kTB = kTH / 8;        // stride-8 row blocks per tile
-constexpr int kHeatRows = kTB + 6;  // stride-8 rows staged for the smoothing window
-constexpr int kPafRows = kTB + 1;   // rows staged for the tile's bilinear row pairs (m0-1 .. m0+tb-1)
+#ifndef EKP_LEAN_TB
+#define EKP_LEAN_TB 3
+#endif
+constexpr int kTB = 2;                    // stride-8 row blocks per tile of the materialising kernel (16 output rows)
+constexpr int kLeanTB = EKP_LEAN_TB;      // ... of the lean kernel: taller tiles, the 6-row halo of the window weighs less
+constexpr int kPafRows = kTB + 1;         // rows staged for the tile's bilinear row pairs (m0-1 .. m0+tb-1)
+template <bool kMat> struct TileBlocks { static constexpr int value = kMat ? kTB : kLeanTB; };  // (+ 6 rows staged for the window)
 
 // Vertical taps of an interior row (no reflect / clamp influence) depend only on Y & 7.
 __constant__ float cTapsInterior[8][8];
@@ -345,14 +348,15 @@ struct TileGeom {
     int pr0, pr1, pc0, pc1;  // staged PAF rows / columns (bilinear row pairs of the tile)
 };
 
+template <int TB>
 __device__ __forceinline__ TileGeom tile_geom(const DenseParams& p, int tile_x, int tile_y, int img) {
     TileGeom g;
     const int h = p.h, w = p.w;
     g.img = img;
-    g.m0 = tile_y * kTB;
+    g.m0 = tile_y * TB;
     g.i0 = tile_x * p.tile_wl;
     g.twl = min(p.tile_wl, w - g.i0);
-    g.tb = min(kTB, h - g.m0);
+    g.tb = min(TB, h - g.m0);
     // the smoothing window of row block m is rows clamp(m-2, 0, h-5) .. +4 (same for columns)
     g.hr0 = max(min(g.m0 - 3, h - 5), 0); g.hr1 = min(max(g.m0 + g.tb + 2, 4), h - 1);
     g.hc0 = max(min(g.i0 - 3, w - 5), 0); g.hc1 = min(max(g.i0 + g.twl + 2, 4), w - 1);
@@ -362,7 +366,7 @@ __device__ __forceinline__ TileGeom tile_geom(const DenseParams& p, int tile_x, 
 }
 
 struct TileSmem {
-    float* heat;    // [kHeatRows][tile_wl + 6][19]
+    float* heat;    // [tile blocks + 6][tile_wl + 6][19]
     float* paf;     // [kPafRows][tile_wl + 2][38]
     float4* store;  // [kStoreBufs][kChunkRows][kChunkCols] float4 (materialising kernel only)
 };
@@ -637,13 +641,13 @@ dense_frontend_kernel(const DenseParams p) {
     const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
     TileSmem sm;
     sm.heat = smem;
-    sm.paf = sm.heat + kHeatRows * hcols * EKP_HEAT_CH;
+    sm.paf = sm.heat + (TileBlocks<kMat>::value + 6) * hcols * EKP_HEAT_CH;
     TileCtl ctl;
     ctl.colmax = sm.paf + (kMat ? kPafRows * pcols * EKP_PAF_CH : 0);  // no PAF patch without materialisation
     ctl.taps = sTaps; ctl.list = sList; ctl.num_active = &sNumActive; ctl.next_task = &sNextTask;
     // store buffers behind the patches, 128-byte aligned (the patches' size is a multiple of 4 bytes only)
     sm.store = reinterpret_cast<float4*>(smem + (((size_t) (ctl.colmax + hcols * EKP_HEAT_CH - smem) + 31) & ~(size_t) 31));
-    const TileGeom g = tile_geom(p, blockIdx.x, blockIdx.y, blockIdx.z);
+    const TileGeom g = tile_geom<TileBlocks<kMat>::value>(p, blockIdx.x, blockIdx.y, blockIdx.z);
     if (!kDebug) {
         // The first wave of CTAs pulls the WHOLE batch's stride-8 inputs into L2 (evict_last) in one burst
         // before the write stream builds up: reads that trickle in between 2.3 GB of stores cost far more than
@@ -678,7 +682,7 @@ dense_frontend_kernel(const DenseParams p) {
 }
 
 size_t dense_frontend_smem_bytes(int tile_wl, bool materialise) {
-    size_t floats = (size_t) kHeatRows * (tile_wl + 6) * EKP_HEAT_CH + (size_t) (tile_wl + 6) * EKP_HEAT_CH;
+    size_t floats = (size_t) ((materialise ? kTB : kLeanTB) + 6) * (tile_wl + 6) * EKP_HEAT_CH + (size_t) (tile_wl + 6) * EKP_HEAT_CH;
     if (!materialise) return sizeof(float) * floats;
     floats += (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH;
     floats = (floats + 31) & ~(size_t) 31;
@@ -705,7 +709,8 @@ cudaError_t configure_dense_frontend() {
 // per-thread stores, 0.408 vs 0.381 ms with the bulk stores and warp roles; see profiles/README.md.)
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
     const size_t smem = dense_frontend_smem_bytes(p.tile_wl, p.paf_mat != nullptr && !p.smooth_out);
-    dim3 grid((p.w + p.tile_wl - 1) / p.tile_wl, (p.h + kTB - 1) / kTB, p.n);
+    const int tb = (p.paf_mat != nullptr && !p.smooth_out) ? kTB : kLeanTB;
+    dim3 grid((p.w + p.tile_wl - 1) / p.tile_wl, (p.h + tb - 1) / tb, p.n);
     if (p.smooth_out) dense_frontend_kernel<false, true><<<grid, kLeanThreads, smem, stream>>>(p);
     else if (p.paf_mat) dense_frontend_kernel<true, false><<<grid, kMatThreads, smem, stream>>>(p);
     else dense_frontend_kernel<false, false><<<grid, kLeanThreads, smem, stream>>>(p);
