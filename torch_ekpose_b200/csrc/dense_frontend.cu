@@ -86,12 +86,15 @@ enum { BAR_FILL = 1, BAR_NMS = 2, BAR_HEAT_READY = 3 };  // named barriers (0 is
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #ifndef EKP_LEAN_TB
-#define EKP_LEAN_TB 3
+#define EKP_LEAN_TB 4
 #endif
 constexpr int kTB = 2;                    // stride-8 row blocks per tile of the materialising kernel (16 output rows)
-constexpr int kLeanTB = EKP_LEAN_TB;      // ... of the lean kernel: taller tiles, the 6-row halo of the window weighs less
+constexpr int kLeanTB = EKP_LEAN_TB;      // ... of the lean kernel for big batches: the 6-row halo of the window weighs less
+                                          // (small batches keep kTB: more, lighter CTAs balance better)
+constexpr int kTaskTB = 2;                // row blocks per NMS task: a tall tile is cut into sub-tiles of this height, so the
+                                          // early-out stays as selective (and the tasks as balanced) as with 16-row tiles
+constexpr int kMaxSubTiles = ((kLeanTB > kTB ? kLeanTB : kTB) + kTaskTB - 1) / kTaskTB;
 constexpr int kPafRows = kTB + 1;         // rows staged for the tile's bilinear row pairs (m0-1 .. m0+tb-1)
-template <bool kMat> struct TileBlocks { static constexpr int value = kMat ? kTB : kLeanTB; };  // (+ 6 rows staged for the window)
 
 // Vertical taps of an interior row (no reflect / clamp influence) depend only on Y & 7.
 __constant__ float cTapsInterior[8][8];
@@ -408,10 +411,13 @@ __device__ __forceinline__ void build_task_list(const DenseParams& p, const Tile
     const int hcols = p.tile_wl + 6;
     const int nstrips = (TW + 29) / 30;
     const unsigned m_strips = magic_of(nstrips);
-    const int ntask = EKP_NUM_PART * nstrips;
+    const int per_sub = EKP_NUM_PART * nstrips;
+    const int ntask = per_sub * ((g.tb + kTaskTB - 1) / kTaskTB);  // task = (sub-tile, part, strip)
     for (int t = tid; t < ntask; t += nthr) {
-        const int c = (int) fastdiv(t, m_strips);
-        const int strip = t - c * nstrips;
+        const int sub = t >= per_sub ? t / per_sub : 0, t_in = t - sub * per_sub;  // (no division in 16-row tiles)
+        const int c = (int) fastdiv(t_in, m_strips);
+        const int strip = t_in - c * nstrips;
+        const int b_lo = sub * kTaskTB, b_hi = min(b_lo + kTaskTB, g.tb);  // this task's row blocks within the tile
         bool active = kDebug || !(p.thr > 0.f);
         if (!active) {
             const int Xa = X0 - 1 + 30 * strip;
@@ -422,7 +428,7 @@ __device__ __forceinline__ void build_task_list(const DenseParams& p, const Tile
             active = mx > p.thr * 0.99999f;
             if (active) {
                 bool any = false;
-                for (int b = 0; b < g.tb && !any; b++) {
+                for (int b = b_lo; b < b_hi && !any; b++) {
                     const int m = g.m0 + b;
                     const int wb = min(max(m - 2, 0), h - 5);
                     const bool interior = m >= 2 && m <= h - 3;
@@ -447,12 +453,14 @@ __device__ __forceinline__ void build_task_list(const DenseParams& p, const Tile
 // below) in registers, 3x3 max NMS, peaks appended to the image's raw list.
 template <bool kDebug>
 __device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g, const float* sHeat, const float* sTaps, int task) {
-    const int img = g.img, m0 = g.m0, tb = g.tb;
     const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
     const int hcols = p.tile_wl + 6;
     const int lane = threadIdx.x & 31;
     const int TW = 8 * g.twl, X0 = 8 * g.i0;
     const int nstrips = (TW + 29) / 30;
+    const int sub = task >= EKP_NUM_PART * nstrips ? task / (EKP_NUM_PART * nstrips) : 0;
+    task -= sub * (EKP_NUM_PART * nstrips);
+    const int img = g.img, m0 = g.m0 + sub * kTaskTB, tb = min(kTaskTB, g.m0 + g.tb - m0);  // rows of this sub-tile
     const float NEG_INF = __int_as_float(0xff800000);
     const int rstride = hcols * EKP_HEAT_CH;
     PeakSink sink;
@@ -629,25 +637,25 @@ __device__ __forceinline__ void process_tile_mat(const DenseParams& p, const Til
     }
 }
 
-template <bool kMat, bool kDebug>
+template <bool kMat, bool kDebug, int TB>
 __global__ void __launch_bounds__(kMat ? kMatThreads : kLeanThreads, kMat ? kMatBlocks : kLeanBlocks)
 dense_frontend_kernel(const DenseParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) float sTaps[64];
-    __shared__ unsigned short sList[EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];
+    __shared__ unsigned short sList[kMaxSubTiles * EKP_NUM_PART * ((8 * kMaxTwl + 29) / 30 + 1)];
     __shared__ int sNumActive, sNextTask;
     if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
     if (threadIdx.x == 0) { sNumActive = 0; sNextTask = 0; }
     const int hcols = p.tile_wl + 6, pcols = p.tile_wl + 2;
     TileSmem sm;
     sm.heat = smem;
-    sm.paf = sm.heat + (TileBlocks<kMat>::value + 6) * hcols * EKP_HEAT_CH;
+    sm.paf = sm.heat + (TB + 6) * hcols * EKP_HEAT_CH;
     TileCtl ctl;
     ctl.colmax = sm.paf + (kMat ? kPafRows * pcols * EKP_PAF_CH : 0);  // no PAF patch without materialisation
     ctl.taps = sTaps; ctl.list = sList; ctl.num_active = &sNumActive; ctl.next_task = &sNextTask;
     // store buffers behind the patches, 128-byte aligned (the patches' size is a multiple of 4 bytes only)
     sm.store = reinterpret_cast<float4*>(smem + (((size_t) (ctl.colmax + hcols * EKP_HEAT_CH - smem) + 31) & ~(size_t) 31));
-    const TileGeom g = tile_geom<TileBlocks<kMat>::value>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+    const TileGeom g = tile_geom<TB>(p, blockIdx.x, blockIdx.y, blockIdx.z);
     if (!kDebug) {
         // The first wave of CTAs pulls the WHOLE batch's stride-8 inputs into L2 (evict_last) in one burst
         // before the write stream builds up: reads that trickle in between 2.3 GB of stores cost far more than
@@ -681,13 +689,14 @@ dense_frontend_kernel(const DenseParams p) {
     else process_tile_lean<kDebug>(p, g, sm, ctl);
 }
 
-size_t dense_frontend_smem_bytes(int tile_wl, bool materialise) {
-    size_t floats = (size_t) ((materialise ? kTB : kLeanTB) + 6) * (tile_wl + 6) * EKP_HEAT_CH + (size_t) (tile_wl + 6) * EKP_HEAT_CH;
+static size_t smem_bytes(int tile_wl, bool materialise, int tb) {
+    size_t floats = (size_t) (tb + 6) * (tile_wl + 6) * EKP_HEAT_CH + (size_t) (tile_wl + 6) * EKP_HEAT_CH;
     if (!materialise) return sizeof(float) * floats;
     floats += (size_t) kPafRows * (tile_wl + 2) * EKP_PAF_CH;
     floats = (floats + 31) & ~(size_t) 31;
     return sizeof(float) * floats + sizeof(float4) * (size_t) kStoreBufs * kStoreBufF4;
 }
+size_t dense_frontend_smem_bytes(int tile_wl, bool materialise) { return smem_bytes(tile_wl, materialise, materialise ? kTB : kLeanTB); }
 // choose the stride-8 tile width: <= kMaxTwl columns, tiles of (nearly) equal width
 int dense_frontend_tile_wl(int w) {
     const int nt = (w + kMaxTwl - 1) / kMaxTwl;
@@ -696,11 +705,10 @@ int dense_frontend_tile_wl(int w) {
 
 // per device, once (ekp_create): allow the largest tile's dynamic shared memory
 cudaError_t configure_dense_frontend() {
-    const int smem = (int) dense_frontend_smem_bytes(kMaxTwl, false);
-    cudaError_t e = cudaFuncSetAttribute(dense_frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) dense_frontend_smem_bytes(kMaxTwl, true));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_frontend_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_frontend_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = raise_dynamic_smem_limit(dense_frontend_kernel<true, false, kTB>, smem_bytes(kMaxTwl, true, kTB));
+    if (e == cudaSuccess) e = raise_dynamic_smem_limit(dense_frontend_kernel<false, false, kTB>, smem_bytes(kMaxTwl, false, kTB));
+    if (e == cudaSuccess) e = raise_dynamic_smem_limit(dense_frontend_kernel<false, false, kLeanTB>, smem_bytes(kMaxTwl, false, kLeanTB));
+    if (e == cudaSuccess) e = raise_dynamic_smem_limit(dense_frontend_kernel<false, true, kTB>, smem_bytes(kMaxTwl, false, kTB));
     return e;
 }
 
@@ -708,12 +716,23 @@ cudaError_t configure_dense_frontend() {
 // patches prefetched into a second buffer -- were measured SLOWER on B200 twice: 0.442 vs 0.412 ms with
 // per-thread stores, 0.408 vs 0.381 ms with the bulk stores and warp roles; see profiles/README.md.)
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
-    const size_t smem = dense_frontend_smem_bytes(p.tile_wl, p.paf_mat != nullptr && !p.smooth_out);
-    const int tb = (p.paf_mat != nullptr && !p.smooth_out) ? kTB : kLeanTB;
-    dim3 grid((p.w + p.tile_wl - 1) / p.tile_wl, (p.h + tb - 1) / tb, p.n);
-    if (p.smooth_out) dense_frontend_kernel<false, true><<<grid, kLeanThreads, smem, stream>>>(p);
-    else if (p.paf_mat) dense_frontend_kernel<true, false><<<grid, kMatThreads, smem, stream>>>(p);
-    else dense_frontend_kernel<false, false><<<grid, kLeanThreads, smem, stream>>>(p);
+    const unsigned gx = (p.w + p.tile_wl - 1) / p.tile_wl;
+    auto grid = [&](int tb) { return dim3(gx, (p.h + tb - 1) / tb, p.n); };
+    if (p.smooth_out) {
+        dense_frontend_kernel<false, true, kTB><<<grid(kTB), kLeanThreads, smem_bytes(p.tile_wl, false, kTB), stream>>>(p);
+    } else if (p.paf_mat) {
+        dense_frontend_kernel<true, false, kTB><<<grid(kTB), kMatThreads, smem_bytes(p.tile_wl, true, kTB), stream>>>(p);
+    } else {
+        // Lean: 16-row tiles balance best while there are few of them; with many waves of tiles taller ones win (their
+        // fixed cost -- staging a 6-row halo, the early-out tables -- is shared by twice the rows).  Same results either way.
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const dim3 g2 = grid(kTB);
+        const bool tall = kLeanTB != kTB && (size_t) g2.x * g2.y * g2.z >= (size_t) 8 * sms * kLeanBlocks;
+        if (tall) dense_frontend_kernel<false, false, kLeanTB><<<grid(kLeanTB), kLeanThreads, smem_bytes(p.tile_wl, false, kLeanTB), stream>>>(p);
+        else dense_frontend_kernel<false, false, kTB><<<g2, kLeanThreads, smem_bytes(p.tile_wl, false, kTB), stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
