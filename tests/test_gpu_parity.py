@@ -483,6 +483,36 @@ def test_small_context_does_not_shrink_kernel_limits_of_a_big_one(ek):
     big.close()
 
 
+def test_part_and_candidate_capacities_are_reported(ek):
+    """More than EKP_MAX_CAND passing pairs on one limb, more than EKP_MAX_PART peaks of one part: flagged per
+    image (EKP_OVF_CANDIDATES / EKP_OVF_PART) and raised, never silently truncated; a clean image in the same
+    batch is unaffected."""
+    H, W = 64, 768
+    paf = np.zeros((3, H, W, 38), np.float32)
+    paf[:, :, :, 12] = 1.0                                  # limb 0 (neck -> RShoulder) x channel: every pair to the right passes
+    def grid(n_a, n_b):
+        rows = [(2 + i, 2 + 2 * (i % 20), 0.9, 0, 1) for i in range(n_a)]           # necks on the left
+        rows += [(300 + i, 2 + 2 * (i % 20), 0.9, 0, 2) for i in range(n_b)]        # right shoulders far to the right
+        return np.array(rows, np.float32)
+    cases = [grid(60, 60), grid(3, 300), grid(2, 2)]      # 3600 candidates; 300 peaks of part 2; fine
+    stride = max(len(c) for c in cases)
+    peaks = np.zeros((3, stride, 5), np.float32)
+    counts = np.array([len(c) for c in cases], np.int32)
+    for i, c in enumerate(cases):
+        peaks[i, :len(c)] = c
+    pp_ = ek.PostProcessor(device=0, max_batch=3, max_h=8, max_w=96, max_peaks=1024, max_humans=512)
+    pp_.run_peaks(_dev(peaks), _dev(counts), _dev(paf), h1=H)
+    with pytest.raises(ek._lib.EkpCapacityError):
+        pp_.results()
+    res = pp_.results(raise_on_overflow=False)
+    assert res["overflow"][0] & ek._lib.OVF_CANDIDATES and not res["overflow"][0] & ek._lib.OVF_PART
+    assert res["overflow"][1] & ek._lib.OVF_PART
+    assert res["overflow"][2] == 0
+    sub, _ = util.oracle_people(cases[2], H, W, paf[2])
+    assert int(res["num_humans"][2]) == len(sub)
+    pp_.close()
+
+
 def test_argument_errors(ek, pp):
     from torch_ekpose_b200 import synthetic
     heat, paf = synthetic.make_batch(1, 46, 54, (1, 1), seed=1)
