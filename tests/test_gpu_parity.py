@@ -306,6 +306,22 @@ def test_config4_crowded_1312x736(pp, frontend):
         assert_bits_equal(res["subset"][0, :len(sub)], sub, "vs compiled reference")
 
 
+@pytest.mark.parametrize("materialize", [True, False])
+def test_large_map_2624x1472(ek, materialize):
+    """A map four times the area of the largest BASELINE shape (184 x 328 stride-8 cells, 12 column tiles): tile
+    geometry, halos and the store chunking far from the shapes the kernels were tuned on, against the oracle."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(1, 184, 328, (20, 20), seed=4)
+    big = ek.PostProcessor(device=0, max_batch=1, max_h=184, max_w=328, max_peaks=2048, max_humans=128)
+    res = _check_batch(big, heat, paf, "dense", materialize, [0])
+    assert int(res["num_humans"][0]) >= 18
+    if materialize:  # and the operator-surface tensors themselves, whole-tensor bit comparison
+        fe = util.frontend()
+        pw = np.ascontiguousarray(paf[0].transpose(1, 2, 0))
+        assert_bits_equal(big.paf_mat[0].cpu().numpy(), fe.upsample_bilinear(pw), "paf_mat")
+    big.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # size-independent properties at full batch sizes
 # ---------------------------------------------------------------------------------------------
