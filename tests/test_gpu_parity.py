@@ -451,6 +451,28 @@ def test_stage45_adversarial_fuzz_vs_oracle(ek, seed):
     small.close()
 
 
+@pytest.mark.parametrize("C,offset", [(38, 0), (38, 1), (39, 0), (40, 0), (41, 3)])
+def test_run_peaks_channel_counts_and_alignment(ek, C, offset):
+    """process_paf indexes paf[ch + f3 * (x + f2 * y)] for any f3 >= 38 (pafprocess.cpp:8): odd channel counts and
+    bases that are only 4-byte aligned take the two-load gather, even ones the 8-byte gather; same people."""
+    rng = np.random.default_rng(C * 10 + offset)
+    H, W = 96, 128
+    peaks, paf38 = _fuzz_scene(rng, H, W, 10, 0.2, 8, [0.0, 0.5, 1.0])
+    paf = rng.normal(0, 1, (H, W, C)).astype(np.float32)
+    paf[:, :, :38] = paf38
+    buf = torch.zeros(paf.size + offset, dtype=torch.float32, device="cuda")
+    view = buf[offset:].view(1, H, W, C)
+    view.copy_(torch.from_numpy(paf)[None])
+    pp_ = ek.PostProcessor(device=0, max_batch=1, max_h=12, max_w=16, max_peaks=1024, max_humans=128)
+    pp_.run_peaks(_dev(peaks[None]), _dev(np.array([len(peaks)], np.int32)), view, h1=H)
+    res = pp_.results()
+    sub, _ = util.oracle_people(peaks, H, W, paf)
+    m = int(res["num_humans"][0])
+    assert m == len(sub) and m > 0
+    assert_bits_equal(res["subset"][0, :m], sub, "subset")
+    pp_.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # capacity and argument errors are reported, never silent
 # ---------------------------------------------------------------------------------------------
