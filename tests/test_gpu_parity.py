@@ -90,6 +90,24 @@ def test_process_paf_golden(ek, scene, upload, monkeypatch):
         assert np.float32(ek.pafprocess.get_part_score(cid)).view(np.uint32) == g["ref_line_score"][cid].view(np.uint32)
 
 
+def test_process_paf_pools_all_p1_images(ek):
+    """peaks[p1, p2, p3]: the reference walks every (p1, p2) row into ONE peak list (pafprocess.cpp:26-36)."""
+    g = golden("c2_46x54_p6")
+    pk = g["ref_peaks"]
+    n = len(pk) // 2 * 2
+    h, w = g["heat"].shape[:2]
+    paf_up = np.repeat(np.repeat(g["paf"], 8, axis=0), 8, axis=1)
+    heat_up = np.zeros((8 * h, 8 * w, 19), np.float32)
+    assert ek.pafprocess.process_paf(pk[None, :n], heat_up, paf_up) == 0
+    flat = _compat_subset(ek)
+    assert ek.pafprocess.process_paf(pk[:n].reshape(2, n // 2, 5), heat_up, paf_up) == 0
+    pooled = _compat_subset(ek)
+    assert flat[0] == pooled[0] > 0 and np.array_equal(flat[1], pooled[1])
+    assert_bits_equal(flat[2], pooled[2], "human scores")
+    sub, _ = util.oracle_people(pk[:n], 8 * h, 8 * w, paf_up)
+    assert flat[0] == len(sub) and np.array_equal(flat[1], sub[:, :18].astype(np.int32))
+
+
 def test_process_paf_rejects_bad_input(ek):
     paf = np.zeros((16, 16, 38), np.float32)
     bad_part = np.array([[(1, 1, .5, 0, 18)]], np.float32)
