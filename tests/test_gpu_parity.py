@@ -524,6 +524,39 @@ def test_inputs_that_are_only_4_byte_aligned(ek):
     pp_.close()
 
 
+@pytest.mark.parametrize("frontend", ["dense", "reference"])
+@pytest.mark.parametrize("shape", [(46, 54), (5, 5), (23, 37), (46, 82), (31, 64)])
+def test_operator_surface_writes_stay_inside_their_tensors(ek, frontend, shape):
+    """compute-sanitizer is not available on the pool, so: heat_mat / paf_mat sit between guard regions filled with a
+    sentinel; after the bulk-store (dense) and nearest-upsample (reference) kernels the guards must be untouched and
+    every element of the tensors written."""
+    from torch_ekpose_b200 import synthetic
+    h, w = shape
+    n = 3
+    heat, paf = synthetic.make_batch(n, h, w, (1, 3), seed=h * 100 + w)
+    G = 4096  # floats per guard, keeps the 16-byte alignment of the tensors
+    nh, npf = n * 64 * h * w * 19, n * 64 * h * w * 38
+    hbuf = torch.full((G + nh + G,), float("nan"), dtype=torch.float32, device="cuda")
+    pbuf = torch.full((G + npf + G,), float("nan"), dtype=torch.float32, device="cuda")
+    pp_ = ek.PostProcessor(device=0, max_batch=n, max_h=h, max_w=w, max_peaks=1024, max_humans=64)
+    lib = ek._lib.lib
+    hd, pd = _dev(heat), _dev(paf)
+    rc = lib.ekp_postprocess(pp_._ctx, hd.data_ptr(), pd.data_ptr(), n, h, w, ek._lib.LAYOUT_NCHW, 0.15,
+                             ek._lib.FRONTEND_DENSE if frontend == "dense" else ek._lib.FRONTEND_REFERENCE,
+                             hbuf.data_ptr() + 4 * G, pbuf.data_ptr() + 4 * G, 0)
+    assert rc == 0, lib.ekp_last_error()
+    torch.cuda.synchronize()
+    for buf, cnt in ((hbuf, nh), (pbuf, npf)):
+        assert torch.isnan(buf[:G]).all() and torch.isnan(buf[G + cnt:]).all(), "a guard region was written"
+        assert not torch.isnan(buf[G:G + cnt]).any(), "part of the tensor was not written"
+    fe = util.frontend()
+    pw = np.ascontiguousarray(paf[1].transpose(1, 2, 0))
+    want = fe.upsample_bilinear(pw) if frontend == "dense" else fe.upsample_nearest(pw)
+    got = pbuf[G:G + npf].view(n, 8 * h, 8 * w, 38)[1].cpu().numpy()
+    assert_bits_equal(got, want, "paf_mat of image 1")
+    pp_.close()
+
+
 def test_small_context_does_not_shrink_kernel_limits_of_a_big_one(ek):
     """Kernel attributes (dynamic shared memory limits) are per device, not per context: creating a context
     with small capacities after a big one must leave the big one working."""
