@@ -86,3 +86,38 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle", text, flags=re.M), f
                 assert "libekp_oracle" not in text and "libpaf_ref" not in text, f
                 assert not re.search(r'#include\s+"[^"]*oracle', text), f
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_abi_example")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tools", "c_abi_example.c"), "-L", os.path.join(root, "torch_ekpose_b200"), "-lekpose_b200",
+           "-Wl,-rpath," + os.path.join(root, "torch_ekpose_b200"), "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ekpose_b200.h compiles as pedantic C99 and a C program links against the library's seven reference
+    symbols; without a GPU it reports EKP_ERR_CUDA (exit 3), with one it prints the known answer."""
+    run = _build_c_example(tmp_path)
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        assert run.returncode == 0 and "humans 1, score 1.500" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 3 and "no CPU fallback" in run.stderr, run.stdout + run.stderr
+
+
+@pytest.mark.gpu
+def test_c_caller_known_answer(tmp_path):
+    """The C99 caller of tools/c_abi_example.c on the GPU: SURVEY.md Appendix A.6 (1 human, score 1.5, x of cid 3 = 40)."""
+    run = _build_c_example(tmp_path)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "humans 1, score 1.500, parts 1..4 -> cids 0 1 2 3, x of cid 3 = 40" in run.stdout
