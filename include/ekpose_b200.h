@@ -25,6 +25,8 @@
 #ifndef EKPOSE_B200_H
 #define EKPOSE_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -57,13 +59,22 @@ typedef enum ekp_frontend {
 
 /* per-image overflow bits reported by ekp_results */
 #define EKP_OVF_PEAKS 1u       /* more peaks than max_peaks */
-#define EKP_OVF_PART 2u        /* more than EKP_MAX_PART peaks of one part */
-#define EKP_OVF_CANDIDATES 4u  /* more than EKP_MAX_CAND passing candidates on one limb */
+#define EKP_OVF_PART 2u        /* more than max_part peaks of one part */
+#define EKP_OVF_CANDIDATES 4u  /* more than max_cand passing candidates on one limb */
 #define EKP_OVF_HUMANS 8u      /* more subset rows than max_humans */
 #define EKP_OVF_BADPEAK 16u    /* a peak had part id outside [0,18) or coordinates outside the PAF map */
 
+/* Default per-image capacities of a context made by ekp_create; ekp_create_ex sets them per context.  The
+ * reference keeps unbounded std::vectors (pafprocess.cpp:24, :47-49); here a scene that exceeds a capacity is
+ * REPORTED (EKP_OVF_*, EKP_ERR_CAPACITY), and the caller re-creates the context with larger ones (the Python
+ * host layer and the process_paf surface grow and retry by themselves). */
 #define EKP_MAX_PART 256       /* peaks of one part per image */
 #define EKP_MAX_CAND 2048      /* candidates that pass both criteria, per limb per image */
+/* hard limits of ekp_create_ex */
+#define EKP_LIMIT_PEAKS 16384
+#define EKP_LIMIT_HUMANS 1024
+#define EKP_LIMIT_PART 1024
+#define EKP_LIMIT_CAND 8192
 
 /* one row of the part-sorted peak table (pafprocess.h:26-31 `Peak`) */
 typedef struct ekp_peak {
@@ -80,6 +91,11 @@ typedef struct ekp_ctx ekp_ctx;
  * and max_humans subset rows per image.  One context = one stream of work; contexts are
  * independent, so one host thread per GPU can drive its own. */
 int ekp_create(ekp_ctx **out, int device, int max_batch, int max_h, int max_w, int max_peaks, int max_humans);
+/* Same with the two remaining capacities explicit (0 = the defaults above): max_part peaks of one part and
+ * max_cand passing candidates of one limb, per image.  Smaller values leave more shared memory per block
+ * (more resident blocks in stage 4), larger ones (up to EKP_LIMIT_*) take scenes the defaults report as overflow. */
+int ekp_create_ex(ekp_ctx **out, int device, int max_batch, int max_h, int max_w, int max_peaks, int max_humans,
+                  int max_part, int max_cand);
 void ekp_destroy(ekp_ctx *ctx);
 const char *ekp_last_error(void);
 const char *ekp_version(void);
@@ -164,7 +180,16 @@ int ekp_last_batch(const ekp_ctx *ctx);   /* images of the last submitted run = 
 int ekp_max_batch(const ekp_ctx *ctx);
 int ekp_max_peaks(const ekp_ctx *ctx);
 int ekp_max_humans(const ekp_ctx *ctx);
+int ekp_max_part(const ekp_ctx *ctx);
+int ekp_max_cand(const ekp_ctx *ctx);
 long long ekp_kernel_launches(const ekp_ctx *ctx); /* kernels launched by this context so far */
+long long ekp_graph_launches(const ekp_ctx *ctx);  /* batches of those that were replayed as a CUDA graph */
+
+/* Pinned (page-locked) host memory for ekp_postprocess_host: when a batch's heat tensor is directly followed by its
+ * PAF tensor in ONE such block the library moves both with a single copy.  write_combined != 0 asks for
+ * write-combined memory (CPU writes only, sequential). */
+int ekp_host_alloc(void **out, size_t bytes, int write_combined);
+int ekp_host_free(void *p);
 
 /* ---- the reference operator surface (lib/pafprocess/pafprocess.h:53-59) ------------------
  * HOST pointers.  peaks [p1,p2,p3] rows (x, y, score, _, part); heatmap [h1,h2,h3] is used only

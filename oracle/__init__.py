@@ -14,9 +14,11 @@ Three checkers:
 * front-ends   -- oracle/frontend_oracle.c: the reference's Python NMS() restated in C, and the
                   dense (north_star) front-end whose arithmetic is defined there.
 
-``reference_python()`` imports the reference's own lib/utils/paf_to_pose.py from
-/root/reference (this container only) with RefPaf injected as ``lib.pafprocess.pafprocess``;
-it is used by tests/golden/make_golden.py to generate the committed fixtures.
+``reference_python()`` imports the reference's own lib/utils/paf_to_pose.py with RefPaf injected as
+``lib.pafprocess.pafprocess`` -- from /root/reference where that tree exists (this container), else
+from oracle/_ref/py, the sourceless bytecode oracle/build_refpy.py compiled from it (a build output
+like the .so; it travels to the GPU box).  tests/golden/make_golden.py uses it to generate the
+committed fixtures, bench.py's reference arm / cpu_baseline to time the UNMODIFIED reference.
 """
 from __future__ import annotations
 
@@ -32,6 +34,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference"
 PORT_SO = os.path.join(HERE, "libekp_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libpaf_ref.so")
+REFPY_ROOT = os.path.join(HERE, "_ref", "py")
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -41,13 +44,26 @@ def build(force: bool = False) -> None:
     """Compile the checkers (gcc only).  Building the checker is not using it."""
     srcs = [os.path.join(HERE, f) for f in ("paf_oracle.c", "frontend_oracle.c", "Makefile")]
     stale = force or not os.path.exists(PORT_SO) or any(os.path.getmtime(s) > os.path.getmtime(PORT_SO) for s in srcs)
-    need_ref = os.path.isdir(REF_ROOT) and (force or not os.path.exists(REF_SO))
+    need_ref = os.path.isdir(REF_ROOT) and (force or not os.path.exists(REF_SO) or not have_refpy())
     if stale or need_ref:
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL)
 
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_refpy() -> bool:
+    """The reference's own Python for the path is importable (source tree or its byte-compiled form)."""
+    return os.path.isfile(os.path.join(REFPY_ROOT, "lib", "utils", "paf_to_pose.bin"))
+
+
+def refpy_root() -> str:
+    if os.path.isfile(os.path.join(REF_ROOT, "lib", "utils", "paf_to_pose.py")):
+        return REF_ROOT
+    if have_refpy():
+        return REFPY_ROOT
+    raise FileNotFoundError("neither /root/reference nor oracle/_ref/py (make -C oracle refpy) is available")
 
 
 class _PafBase:
@@ -287,27 +303,106 @@ def subset_of(paf_impl: _PafBase, peaks_n5: np.ndarray, H: int, W: int, paf_mat:
     return paf_impl.subset(), paf_impl.peaks_line()
 
 
-def reference_python(use_ref: bool = True):
-    """Import the reference's own lib/utils/paf_to_pose.py (this container only).
+def reference_cfg():
+    """lib.config needs yacs (absent), so cfg is a SimpleNamespace with the values of lib/config/default.py:16-25;
+    cfg is passed as an argument by every caller (paf_to_pose.py:346)."""
+    ns = types.SimpleNamespace
+    return ns(MODEL=ns(NUM_KEYPOINTS=18, DOWNSAMPLE=8),
+              TEST=ns(THRESH_HEATMAP=0.15, THRESH_PAF=0.05, NUM_INTERMED_PTS_BETWEEN_KEYPOINTS=10))
 
-    Returns (paf_to_pose_module, cfg_namespace, paf_impl).  lib.config needs yacs (absent),
-    so cfg is a SimpleNamespace with the values of lib/config/default.py:16-25; cfg is passed
-    as an argument by every caller (paf_to_pose.py:346).
-    """
-    if not os.path.isdir(REF_ROOT):
-        raise FileNotFoundError("/root/reference is not available on this machine")
-    impl = RefPaf() if use_ref else PortPaf()
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+
+class _RefPyFinder:
+    """Imports ``lib.*`` from the byte-compiled reference under oracle/_ref/py: packages are the directories there
+    (the reference has no lib/__init__.py either), modules the ``<name>.bin`` files build_refpy.py wrote."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname != "lib" and not fullname.startswith("lib."):
+            return None
+        base = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(base + ".bin"):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, base + ".bin")
+            return importlib.util.spec_from_file_location(fullname, base + ".bin", loader=loader)
+        if os.path.isdir(base):
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        return None
+
+
+def _reference_path(root=None) -> str:
+    root = root or refpy_root()
+    if os.path.isfile(os.path.join(root, "lib", "utils", "paf_to_pose.bin")):   # the byte-compiled form
+        if not any(isinstance(f, _RefPyFinder) and f.root == root for f in sys.meta_path):
+            sys.meta_path.insert(0, _RefPyFinder(root))
+    elif root not in sys.path:
+        sys.path.insert(0, root)
     import warnings
     warnings.filterwarnings("ignore", category=DeprecationWarning)
-    import lib.pafprocess as pkg  # namespace package: there is no lib/__init__.py
+    return root
+
+
+def reference_python(use_ref: bool = True, root=None):
+    """Import the reference's own lib/utils/paf_to_pose.py, unmodified.
+
+    Returns (paf_to_pose_module, cfg_namespace, paf_impl).  The SWIG module the reference imports
+    (paf_to_pose.py:7) is replaced by a ctypes view of the compiled reference C++ (RefPaf) -- SWIG is
+    absent and adds no arithmetic.  ``root`` forces /root/reference or oracle/_ref/py.
+    """
+    _reference_path(root)
+    impl = RefPaf() if use_ref else PortPaf()
     mod = impl.as_module()
+    pkg = sys.modules.get("lib.pafprocess")
+    if pkg is None:   # there is no importable lib/pafprocess package (no __init__, SWIG output absent): a stub holds the module
+        pkg = types.ModuleType("lib.pafprocess")
+        pkg.__path__ = []
+        sys.modules["lib.pafprocess"] = pkg
     sys.modules["lib.pafprocess.pafprocess"] = mod
     pkg.pafprocess = mod
     from lib.utils import paf_to_pose  # noqa: E402
     paf_to_pose.pafprocess = mod
-    ns = types.SimpleNamespace
-    cfg = ns(MODEL=ns(NUM_KEYPOINTS=18, DOWNSAMPLE=8),
-             TEST=ns(THRESH_HEATMAP=0.15, THRESH_PAF=0.05, NUM_INTERMED_PTS_BETWEEN_KEYPOINTS=10))
-    return paf_to_pose, cfg, impl
+    return paf_to_pose, reference_cfg(), impl
+
+
+def reference_module(name: str, root=None):
+    """Any other byte-compiled reference module, unmodified: 'lib.network.vgg2016', 'lib.evaluate.estimator',
+    'lib.datasets.preprocessing', 'lib.utils.common'."""
+    import importlib
+    _reference_path(root)
+    return importlib.import_module(name)
+
+
+def dense_restatement_libs(heat_hwc: np.ndarray, paf_hwc: np.ndarray, impl: _PafBase, thr: float = 0.15):
+    """BASELINE.md section 4's "dense restatement": the north_star stages 1-3 with the library primitives the
+    reference itself imports (paf_to_pose.py:1-6) -- cv2.resize(INTER_LINEAR) x8 of heat and PAF,
+    scipy.ndimage.gaussian_filter(sigma=3) on the 18 part maps, maximum_filter(size=3) + threshold -- followed by
+    ``impl.process_paf`` and the getter loop.  The like-for-like CPU line of the dense GPU arm (the GPU computes
+    the same operator in float32 polyphase form; peak SETS agree, tests/test_oracle_pinning.py).
+    Returns (peaks[N,5], number of humans)."""
+    import cv2
+    from scipy.ndimage import gaussian_filter, maximum_filter
+    heat_up = cv2.resize(heat_hwc, None, fx=8, fy=8, interpolation=cv2.INTER_LINEAR)
+    paf_up = cv2.resize(paf_hwc, None, fx=8, fy=8, interpolation=cv2.INTER_LINEAR)
+    rows = []
+    for k in range(18):
+        g = gaussian_filter(heat_up[:, :, k], sigma=3)
+        pk = (maximum_filter(g, size=3) == g) & (g > np.float32(thr))
+        ys, xs = np.nonzero(pk)
+        for y, x in zip(ys, xs):
+            rows.append((x, y, g[y, x], len(rows), k))
+    peaks = np.asarray(rows, np.float32).reshape(-1, 5)
+    n = 0
+    if len(peaks):
+        impl.process_paf(peaks[None], heat_up, paf_up)
+        n = impl.get_num_humans()
+        for hid in range(n):
+            for part in range(18):
+                cid = impl.get_part_cid(hid, part)
+                if cid >= 0:
+                    impl.get_part_x(cid), impl.get_part_y(cid), impl.get_part_score(cid)
+            impl.get_score(hid)
+    return peaks, n

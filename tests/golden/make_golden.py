@@ -124,7 +124,52 @@ def kat_fixture(ref):
     np.savez_compressed(os.path.join(OUT, "kat.npz"), **d)
 
 
+def reference_append_result():
+    """The reference's OWN append_result (eval.py:93-125) and ORDER_COCO (eval.py:35), taken from its source with `ast`
+    (importing eval.py would pull in pycocotools, absent here) and executed unmodified."""
+    import ast
+    src = open(os.path.join(oracle.REF_ROOT, "eval.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.FunctionDef) and n.name == "append_result")
+            or (isinstance(n, ast.Assign) and any(getattr(t, "id", None) == "ORDER_COCO" for t in n.targets))]
+    assert len(keep) == 2, "eval.py no longer has append_result / ORDER_COCO at module level"
+    ns = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "eval.py (append_result, ORDER_COCO)", "exec"), ns)
+    return ns["append_result"], ns["ORDER_COCO"]
+
+
+def coco_fixture():
+    """Row f3: what the reference's append_result produces from the reference's paf_to_pose_cpp humans on the golden
+    scenes (OpenCV's own bicubic code; the coordinates do not depend on IPP).  The inputs are the committed scene
+    fixtures, so this can be regenerated without touching them."""
+    append_result, order = reference_append_result()
+    p2p, cfg, ref = oracle.reference_python()
+    cv2.ipp.setUseIPP(False)
+    d = {"ORDER_COCO": np.asarray(order, np.int32)}
+    ups_by_scene = {"c1_46x54_p3": (368 / 0.77, 432 / 0.77), "c2_46x54_p6": (368.0, 432.0), "c3_46x82_p8": (480.0, 853.0),
+                    "c4_crowd_64x96_p24": (512 / 1.3, 768 / 1.3), "empty_46x54": (368.0, 432.0)}
+    for image_id, (name, ups) in enumerate(ups_by_scene.items()):
+        with np.load(os.path.join(OUT, name + ".npz")) as z:
+            heat, paf = z["heat"], z["paf"]
+        humans = p2p.paf_to_pose_cpp(heat, paf, cfg)
+        outputs = []
+        append_result(100 + image_id, humans, ups, outputs)
+        d[name + "_upsample_keypoints"] = np.asarray(ups, np.float64)
+        d[name + "_image_id"] = np.asarray(100 + image_id)
+        d[name + "_keypoints"] = np.asarray([o["keypoints"] for o in outputs], np.float64).reshape(len(outputs), 51)
+        d[name + "_score"] = np.asarray([o["score"] for o in outputs], np.float64)
+        d[name + "_category_id"] = np.asarray([o["category_id"] for o in outputs], np.int64)
+        print("coco", name, "results", len(outputs))
+    cv2.ipp.setUseIPP(True)
+    np.savez_compressed(os.path.join(OUT, "coco_append_result.npz"), **d)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "coco":   # only the f3 fixture (reads the committed scenes)
+        oracle.build()
+        coco_fixture()
+        return
     oracle.build(force=True)
     p2p, cfg, ref = oracle.reference_python()
     fe = oracle.Frontend()
@@ -139,6 +184,7 @@ def main():
     for name, (heat, paf) in scenes.items():
         scene_fixture(name, heat, paf, p2p, cfg, ref, fe)
     kat_fixture(ref)
+    coco_fixture()
 
 
 if __name__ == "__main__":

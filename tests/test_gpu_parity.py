@@ -298,7 +298,7 @@ def _check_batch(pp, heat, paf, frontend, materialize, images):
 def test_config2_batch64_368x432(pp, frontend, materialize):
     from torch_ekpose_b200 import synthetic
     heat, paf = synthetic.make_batch(64, 46, 54, (1, 6), seed=2)
-    res = _check_batch(pp, heat, paf, frontend, materialize, range(0, 64, 3))
+    res = _check_batch(pp, heat, paf, frontend, materialize, range(64))   # every image of the batch
     assert res["num_humans"].sum() > 150
 
 
@@ -306,7 +306,18 @@ def test_config2_batch64_368x432(pp, frontend, materialize):
 def test_config3_656x368(pp, frontend):
     from torch_ekpose_b200 import synthetic
     heat, paf = synthetic.make_batch(32, 46, 82, (2, 8), seed=3)
-    _check_batch(pp, heat, paf, frontend, frontend == "dense", range(0, 32, 3))
+    _check_batch(pp, heat, paf, frontend, frontend == "dense", range(32))
+
+
+@pytest.mark.parametrize("frontend,materialize", [("dense", True), ("dense", False), ("reference", False)])
+def test_config3_full_batch_256(ek, frontend, materialize):
+    """configs[2] at its full size: 256 frames of 656x368 in ONE batch, every image checked against the oracle."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(256, 46, 82, (2, 8), seed=33)
+    big = ek.PostProcessor(device=0, max_batch=256, max_h=46, max_w=82, max_peaks=1024, max_humans=32, max_part=64, max_cand=512)
+    res = _check_batch(big, heat, paf, frontend, materialize, range(256))
+    assert res["num_humans"].sum() > 1000
+    big.close()
 
 
 @pytest.mark.parametrize("frontend", ["dense", "reference"])
@@ -665,14 +676,106 @@ def test_batched_handoff_from_the_network(ek):
             return (torch.from_numpy(paf).to(x.device), torch.from_numpy(heat).to(x.device)), None
 
     frames = [np.zeros((368, 432, 3), np.uint8) for _ in range(3)]
-    got = estimator.infer_humans(frames, FakeNet(), "vgg", torch.device("cuda", 0))
+    dev = torch.device("cuda", torch.cuda.device_count() - 1)   # the tensors' device decides, not device 0
+    got = estimator.infer_humans(frames, FakeNet(), "vgg", dev)
+    assert estimator.last_postprocessor().device == dev.index
+    fe = util.frontend()
     for i in range(3):
-        want = ek.paf_to_pose_cpp(heat[i].transpose(1, 2, 0), paf[i].transpose(1, 2, 0), ek.cfg)
-        assert len(got[i]) == len(want) > 0
-        for a, b in zip(got[i], want):
-            assert a.score == b.score and sorted(a.body_parts) == sorted(b.body_parts)
-            assert all((a.body_parts[k].x, a.body_parts[k].y, a.body_parts[k].score) ==
-                       (b.body_parts[k].x, b.body_parts[k].y, b.body_parts[k].score) for k in a.body_parts)
+        # the ORACLE on the same maps: reference front-end restatement + the compiled reference process_paf, then the
+        # getter loop of paf_to_pose_cpp (paf_to_pose.py:361-377) restated on its tables
+        hw, pw = np.ascontiguousarray(heat[i].transpose(1, 2, 0)), np.ascontiguousarray(paf[i].transpose(1, 2, 0))
+        peaks = fe.ref_nms(hw)
+        sub, line = util.oracle_people(peaks, 368, 432, fe.upsample_nearest(pw))
+        assert len(got[i]) == len(sub) > 0
+        for hm, row in zip(got[i], sub):
+            assert np.float32(hm.score) == np.float32(row[18]) / np.float32(row[19])
+            cids = {k: int(row[k]) for k in range(18) if int(row[k]) >= 0}
+            assert sorted(hm.body_parts) == sorted(cids)
+            for k, cid in cids.items():
+                bp = hm.body_parts[k]
+                assert (bp.x, bp.y) == (float(line[0][cid]) / 432, float(line[1][cid]) / 368)
+                assert np.float32(bp.score) == line[2][cid] and bp.uidx == "%d-%d" % (got[i].index(hm), k)
+
+
+@pytest.mark.parametrize("scene", util.SCENES)
+def test_coco_results_equal_the_reference_append_result(ek, pp, scene):
+    """Row f3 end to end on the GPU: maps -> CUDA post-processing (reference front-end) -> vectorised COCO conversion must
+    equal what the reference's own append_result (eval.py:93-125, executed unmodified by make_golden.py) produced from the
+    reference's paf_to_pose_cpp humans."""
+    from torch_ekpose_b200 import coco
+    fx = golden("coco_append_result")
+    g = golden(scene)
+    h, w = g["heat"].shape[:2]
+    pp.run(_dev(_nchw(g["heat"])), _dev(_nchw(g["paf"])), frontend="reference")
+    num, parts, _ = pp.human_tables()
+    got = coco.coco_results([int(fx[scene + "_image_id"])], num, parts, (8 * h, 8 * w), tuple(fx[scene + "_upsample_keypoints"]))
+    want = fx[scene + "_keypoints"]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(np.asarray(a["keypoints"], np.float64).view(np.uint64), b.view(np.uint64))
+        assert a["score"] == 1.0 and a["category_id"] == 1
+
+
+def test_repeated_batches_replay_as_cuda_graphs(ek):
+    """A batch with the same pointers, shape and flags as an earlier one is one graph launch; results equal the eager
+    first submission bit for bit, on the device entry and on the host entry (one pinned block, one copy)."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(8, 46, 54, (2, 5), seed=77)
+    p = ek.PostProcessor(device=0, max_batch=8, max_h=46, max_w=54, max_peaks=1024, max_humans=32)
+    hd, pd = _dev(heat), _dev(paf)
+    outs = []
+    for rep in range(3):
+        for frontend, mat in (("dense", True), ("dense", False), ("reference", False)):
+            p.run(hd, pd, frontend=frontend, materialize=mat)
+            outs.append((rep, frontend, mat, p.results(with_peaks=True)))
+    assert p.graph_launches() >= 6   # the second and third round at least (the first captures)
+    pb = ek.PinnedBatch(8, 46, 54)
+    np.copyto(pb.heat, heat); np.copyto(pb.paf, paf)
+    for rep in range(3):
+        p.run(pb.heat, pb.paf, frontend="dense", materialize=True)
+        outs.append((rep, "dense", True, p.results(with_peaks=True)))
+    first = {}
+    for rep, frontend, mat, res in outs:
+        ref = first.setdefault((frontend, mat), res)
+        for key in ("num_humans", "n_peaks", "overflow"):
+            assert np.array_equal(ref[key], res[key])
+        assert_bits_equal(ref["subset"], res["subset"], f"{frontend} {mat} rep {rep}")
+        assert np.array_equal(ref["peaks"], res["peaks"])
+    _check_batch(p, heat, paf, "dense", True, range(8))
+    pb.close()
+    p.close()
+
+
+def test_context_capacities_and_growth(ek):
+    """max_part / max_cand are per-context capacities (ekp_create_ex): a crowd overflows a small context (reported,
+    never silent) and fits a big one; postprocess_batch grows the capacities that overflowed and retries, within the
+    library's limits."""
+    from torch_ekpose_b200 import _lib, synthetic
+    heat, paf = synthetic.make_batch(1, 92, 164, (35, 35), seed=9)
+    small = ek.PostProcessor(device=0, max_batch=1, max_h=92, max_w=164, max_peaks=2048, max_humans=128, max_part=16, max_cand=64)
+    assert (small.max_part, small.max_cand) == (16, 64)
+    small.run(_dev(heat), _dev(paf), frontend="reference")
+    res = small.results(raise_on_overflow=False)
+    assert int(res["overflow"][0]) & _lib.OVF_PART
+    with pytest.raises(_lib.EkpCapacityError):
+        small.results()
+    small.close()
+    big = ek.PostProcessor(device=0, max_batch=1, max_h=92, max_w=164, max_peaks=2048, max_humans=128, max_part=512, max_cand=4096)
+    _check_batch(big, heat, paf, "reference", False, [0])
+    big.close()
+    for bad in (dict(max_part=2048), dict(max_cand=16), dict(max_humans=2048), dict(max_peaks=100000), dict(max_batch=70000)):
+        kw = dict(device=0, max_batch=1, max_h=8, max_w=8, max_peaks=64, max_humans=8)
+        kw.update(bad)
+        with pytest.raises(_lib.EkpError):
+            ek.PostProcessor(**kw)
+    # the convenience API starts small and grows what overflowed
+    from torch_ekpose_b200 import paf_to_pose
+    paf_to_pose._cache.clear()
+    humans = ek.postprocess_batch(heat, paf, frontend="reference", max_peaks=256, max_humans=8, max_part=8, max_cand=64)
+    hw, pw = np.ascontiguousarray(heat[0].transpose(1, 2, 0)), np.ascontiguousarray(paf[0].transpose(1, 2, 0))
+    _, sub = util.oracle_reference(hw, pw)
+    assert len(humans[0]) == len(sub) >= 30
+    paf_to_pose._cache.clear()
 
 
 def test_random_shapes_layouts_thresholds_vs_oracle(ek):

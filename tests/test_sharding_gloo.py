@@ -67,3 +67,45 @@ def test_sharded_equals_single_process(tmp_path, n_images):
         assert np.array_equal(z["num"], want_num)
         assert np.array_equal(z["sub"].view(np.uint32), want_sub.view(np.uint32))
     assert want_num.sum() >= n_images
+
+
+def _failing_worker(rank, world, port, mode, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from torch_ekpose_b200 import synthetic
+    from torch_ekpose_b200.sharding import ShardError, postprocess_sharded
+    heat, paf = synthetic.make_batch(4, 46, 54, (1, 2), seed=6)
+
+    def compute(hs, ps):
+        num, sub = _oracle_compute(hs, ps)
+        if mode == "raise" and rank == 1:
+            raise RuntimeError("device lost on this rank")
+        ovf = np.zeros(len(num), np.uint32)
+        if mode == "overflow" and rank == 0:
+            ovf[1] = 4   # EKP_OVF_CANDIDATES on global image 1
+        return num, sub, ovf
+
+    try:
+        postprocess_sharded(heat, paf, max_humans=32, compute=compute)
+        outcome = "returned"
+    except ShardError as e:
+        outcome = str(e)
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write(outcome)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["raise", "overflow"])
+def test_a_failing_rank_fails_every_rank_after_the_gather(tmp_path, mode):
+    """A rank whose shard raised (or overflowed a capacity) must not leave the others waiting in the collective:
+    the status and overflow bits travel with the tables and EVERY rank raises afterwards."""
+    world = 2
+    mp.spawn(_failing_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
+    texts = [open(tmp_path / f"rank{r}.txt").read() for r in range(world)]
+    for t in texts:
+        assert t != "returned" and "sharded post-processing failed" in t
+    if mode == "raise":
+        assert all("ranks with errors [1]" in t for t in texts) and "device lost" in texts[1] and "device lost" not in texts[0]
+    else:
+        assert all("capacity overflow [1]" in t and "0x4" in t for t in texts)

@@ -61,8 +61,10 @@ def peaks_table(res, i):
 
 
 def oracle_people(peaks_n5, H, W, paf_mat, impl=None):
-    """subset rows for one image from the C restatement (or the compiled reference)."""
-    impl = impl or port()
+    """subset rows for one image: from the COMPILED REFERENCE (oracle/_ref/libpaf_ref.so, lib/pafprocess/pafprocess.cpp
+    unmodified) wherever it was built -- it travels to the GPU box -- else from its C restatement (pinned to it bit
+    for bit by tests/test_oracle_pinning.py)."""
+    impl = impl or ref_or_none() or port()
     sub, line = oracle.subset_of(impl, np.ascontiguousarray(peaks_n5, np.float32), H, W, paf_mat)
     return sub, line
 

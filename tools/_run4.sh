@@ -1,0 +1,5 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_b.log 2>&1
+tail -3 gpurun_out/r2_pytest_b.log
+python tools/time_configs.py > gpurun_out/r2_time_configs_b.log 2>&1
+EKPOSE_B200_SO=build/variants/asmprof.so python tools/asm_profile.py > gpurun_out/r2_asm_profile_b.log 2>&1
+EKPOSE_B200_SO=build/variants/connprof.so python tools/conn_profile.py > gpurun_out/r2_conn_profile_b.log 2>&1

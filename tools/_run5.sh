@@ -1,0 +1,7 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_c.log 2>&1
+tail -3 gpurun_out/r2_pytest_c.log
+python tools/time_configs.py > gpurun_out/r2_time_configs_c.log 2>&1
+EKPOSE_B200_SO=build/variants/asmprof.so python tools/asm_profile.py > gpurun_out/r2_asm_profile_c.log 2>&1
+EKPOSE_B200_SO=build/variants/connprof.so python tools/conn_profile.py > gpurun_out/r2_conn_profile_c.log 2>&1
+( time python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_c.json 2> gpurun_out/r2_bench_c.err ) 2> gpurun_out/r2_bench_c.time
+tail -3 gpurun_out/r2_bench_c.err

@@ -1,5 +1,5 @@
 """Per-phase times inside assemble_kernel (needs a library built with -DEKP_ASM_PROFILE:
-VARIANT_SRC=assemble.cu tools/build_variants.sh prof "-DEKP_ASM_PROFILE"; EKPOSE_B200_SO=build/variants/prof.so)."""
+VARIANT_SRC=assemble.cu tools/build_variants.sh asmprof "-DEKP_ASM_PROFILE"; EKPOSE_B200_SO=build/variants/asmprof.so)."""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,9 +16,9 @@ def run(label, n, h, w, people, frontend, materialize):
     lib.ekp_debug_asm_profile(buf, 1)
     pp.run(hd, pd, frontend=frontend, materialize=materialize); pp.results()
     lib.ekp_debug_asm_profile(buf, 1)
-    print(f"{label}: per image: staging {buf[0]/n/1e3:.2f} us, limbs tried in parallel {buf[1]/n/1e3:.2f} us, sequential limbs {buf[2]/n/1e3:.2f} us, "
-          f"prune+record {buf[3]/n/1e3:.2f} us; limbs parallel {buf[4]/n:.1f} sequential {buf[5]/n:.1f}; "
-          f"slowest image {buf[6]/1e3:.1f} us, most sequential limbs in one image {buf[7]}")
+    u = lambda k: buf[k] / n / 1e3
+    print(f"{label}: per image (us): staging {u(0):.2f} | limbs total {u(1):.2f} = lookup+simple {u(3):.2f} + complex walk {u(4):.2f} + new rows {u(5):.2f} "
+          f"| prune+record {u(2):.2f}; complex connections per image {buf[6]/n:.1f}, map rebuilds per image {buf[7]/n:.1f}")
     pp.close()
 run("C4 crowded dense lean", 16, 92, 164, (30, 40), "dense", False)
 run("C4 crowded reference lean", 16, 92, 164, (30, 40), "reference", False)

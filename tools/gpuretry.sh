@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: gpuretry.sh <outfile> <timeout> <cmd>
+out=$1; to=$2; shift 2
+for i in 1 2 3 4 5 6 7 8 9 10 11 12; do
+  /usr/local/graft/bin/gpurun --timeout $to -- "$@" > $out 2>&1
+  rc=$?
+  if [ $rc -ne 3 ] && ! grep -q "status=transient" $out; then exit $rc; fi
+  sleep 120
+done
+exit 3

@@ -15,7 +15,7 @@ is no CPU fallback.
 from . import _lib, pafprocess  # noqa: F401
 from .common import BodyPart, CocoPairs, CocoPart, Human  # noqa: F401
 from .config import cfg  # noqa: F401
-from .paf_to_pose import NMS, PostProcessor, compute_resized_coords, find_peaks, paf_to_pose_cpp, postprocess_batch  # noqa: F401
+from .paf_to_pose import NMS, PinnedBatch, PostProcessor, compute_resized_coords, find_peaks, paf_to_pose_cpp, postprocess_batch  # noqa: F401
 
-__all__ = ["pafprocess", "paf_to_pose_cpp", "NMS", "find_peaks", "compute_resized_coords", "PostProcessor", "postprocess_batch", "Human", "BodyPart",
+__all__ = ["pafprocess", "paf_to_pose_cpp", "NMS", "find_peaks", "compute_resized_coords", "PostProcessor", "PinnedBatch", "postprocess_batch", "Human", "BodyPart",
            "CocoPart", "CocoPairs", "cfg"]

@@ -18,6 +18,8 @@ LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 FRONTEND_DENSE, FRONTEND_REFERENCE, FRONTEND_REFERENCE_COARSE = 0, 1, 2
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
 OVF_PEAKS, OVF_PART, OVF_CANDIDATES, OVF_HUMANS, OVF_BADPEAK = 1, 2, 4, 8, 16
+MAX_PART, MAX_CAND = 256, 2048                                              # EKP_MAX_PART / EKP_MAX_CAND (defaults)
+LIMIT_PEAKS, LIMIT_HUMANS, LIMIT_PART, LIMIT_CAND = 16384, 1024, 1024, 8192  # EKP_LIMIT_*
 
 
 class EkpError(RuntimeError):
@@ -38,6 +40,7 @@ class Peak(C.Structure):  # ekp_peak
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
     "ekp_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
+    "ekp_create_ex": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i]),
     "ekp_destroy": (None, [_vp]),
     "ekp_last_error": (C.c_char_p, []),
     "ekp_version": (C.c_char_p, []),
@@ -57,7 +60,12 @@ SIGNATURES = {
     "ekp_max_batch": (_i, [_vp]),
     "ekp_max_peaks": (_i, [_vp]),
     "ekp_max_humans": (_i, [_vp]),
+    "ekp_max_part": (_i, [_vp]),
+    "ekp_max_cand": (_i, [_vp]),
     "ekp_kernel_launches": (C.c_longlong, [_vp]),
+    "ekp_graph_launches": (C.c_longlong, [_vp]),
+    "ekp_host_alloc": (_i, [C.POINTER(_vp), C.c_size_t, _i]),
+    "ekp_host_free": (_i, [_vp]),
     # the reference operator surface, lib/pafprocess/pafprocess.h:53-59
     "process_paf": (_i, [_i, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "get_num_humans": (_i, []),

@@ -27,16 +27,15 @@ cudaError_t launch_upsample_nearest(const float* lo, int layout, int n, int h, i
 cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fixed, int peaks_stride, int p3, int n, int W,
                                 int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow, cudaStream_t stream);
 cudaError_t configure_peaks_sort(int raw_cap);
-cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int id_from_key, int n, ekp_peak* line,
-                              int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
-cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int max_peaks, const PafSource& paf, int h1, int n,
-                               Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream);
-cudaError_t configure_assemble(int max_humans, int max_peaks);
-cudaError_t launch_assemble(const ekp_peak* line, int max_peaks, const int* n_peaks, const Conn* conns, const int* n_conns,
-                            int max_humans, int n, const unsigned* overflow, unsigned char* records, const ResultLayout& lay,
-                            cudaStream_t stream);
+cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int max_part, int id_from_key, int n,
+                              ekp_peak* line, int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
+cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w);
+cudaError_t launch_paf_connect(const ConnectParams& P, int n, cudaStream_t stream);
+cudaError_t configure_assemble(int max_humans, int max_peaks, int max_part);
+cudaError_t launch_assemble(AsmParams P, int n, cudaStream_t stream);
 cudaError_t launch_pair_sample_offsets(const ekp_peak* line, const int* part_off, const int* pair_base, int H, int W, int C,
-                                       unsigned* offs, cudaStream_t stream);
+                                       int max_part, unsigned* offs, cudaStream_t stream);
+size_t debug_std_sort_scratch_words(int n);
 cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned* scratch, cudaStream_t stream);
 cudaError_t launch_preprocess(const unsigned char* src, float* out, const int* xofs, const short* ialpha, const int* yofs,
                               const short* ibeta, int n, int sh, int sw, int rh, int rw, int ph, int pw, int mode,
@@ -122,8 +121,26 @@ static void build_cubic_table(float* tab /* [8][4] */) {
 }
 
 // ---- context -----------------------------------------------------------------------------------
+// arguments of one batch submission (also the key of its CUDA graph)
+struct PostArgs {
+    const float *heat, *paf;            // device inputs
+    const float *heat_host, *paf_host;  // host inputs to copy in first (nullptr: the device pointers are the caller's)
+    size_t h2d_heat_bytes, h2d_paf_bytes;
+    int n, h, w, layout, frontend;
+    float thr;
+    float *heat_mat, *paf_mat;
+};
+static bool same_args(const PostArgs& a, const PostArgs& b) {
+    return a.heat == b.heat && a.paf == b.paf && a.heat_host == b.heat_host && a.paf_host == b.paf_host && a.n == b.n && a.h == b.h &&
+           a.w == b.w && a.layout == b.layout && a.frontend == b.frontend && memcmp(&a.thr, &b.thr, sizeof(float)) == 0 &&
+           a.heat_mat == b.heat_mat && a.paf_mat == b.paf_mat;
+}
+
+struct GraphEntry { PostArgs key; cudaGraphExec_t exec; int kernels; unsigned long long stamp; };
+
 struct ekp_ctx {
     int device = 0, max_batch = 0, max_h = 0, max_w = 0, max_peaks = 0, max_humans = 0;
+    int max_part = EKP_MAX_PART, max_cand = EKP_MAX_CAND;  // peaks of one part / passing candidates of one limb, per image
     // device work buffers
     RawPeak* raw = nullptr;
     int* raw_count = nullptr;       // [max_batch]
@@ -131,12 +148,11 @@ struct ekp_ctx {
     ekp_peak* line = nullptr;       // [max_batch][max_peaks]
     int* part_off = nullptr;        // [max_batch][20]
     int* n_peaks = nullptr;         // [max_batch]
-    Conn* conns = nullptr;          // [max_batch][19][EKP_MAX_PART]
+    Conn* conns = nullptr;          // [max_batch][19][max_part]
     int* n_conns = nullptr;         // [max_batch][19]
     unsigned char* records = nullptr;  // [max_batch] packed result records (ResultLayout)
     ResultLayout lay = {};
-    float* in_heat = nullptr;       // staging for the host-buffer entry points
-    float* in_paf = nullptr;
+    float* in_block = nullptr;      // staging for the host-buffer entry point: [heat | paf] of one batch, contiguous
     float* mat_heat = nullptr;      // context-owned operator-surface tensors (host entry, lazily)
     float* mat_paf = nullptr;
     size_t mat_images = 0, mat_hw = 0;
@@ -154,6 +170,12 @@ struct ekp_ctx {
     int last_n = 0;
     bool has_run = false;
     long long launches = 0;
+    // CUDA graphs of repeated batches (submit_batch)
+    std::vector<GraphEntry>* graphs = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    bool graphs_ok = true;
+    unsigned long long graph_clock = 0;
+    long long graph_launches = 0;
     // optional per-stage timing: events recorded on the work stream around each stage
     static const int kRing = 64;
     bool timing = false;
@@ -169,10 +191,12 @@ static int ctx_free(ekp_ctx* c) {
     if (!c) return EKP_OK;
     cudaSetDevice(c->device);
     void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->records,
-                   c->in_heat, c->in_paf, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic, c->prep_tab};
+                   c->in_block, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic, c->prep_tab};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {c->h_records, c->h_line};
     for (void* p : host) if (p) cudaFreeHost(p);
+    if (c->graphs) { for (GraphEntry& e : *c->graphs) cudaGraphExecDestroy(e.exec); delete c->graphs; }
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->done) cudaEventDestroy(c->done);
     for (auto& row : c->tev) for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
     delete c;
@@ -180,11 +204,20 @@ static int ctx_free(ekp_ctx* c) {
 }
 
 extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, int max_w, int max_peaks, int max_humans) {
+    return ekp_create_ex(out, device, max_batch, max_h, max_w, max_peaks, max_humans, 0, 0);
+}
+
+extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h, int max_w, int max_peaks, int max_humans,
+                             int max_part, int max_cand) {
     if (!out) return fail(EKP_ERR_ARG, "ekp_create: out is NULL");
     *out = nullptr;
-    if (max_batch < 1 || max_h < 5 || max_w < 5 || max_peaks < 1 || max_humans < 1 || max_peaks > 16384 || max_humans > 1024)
-        return fail(EKP_ERR_ARG, "ekp_create: bad capacity (batch %d, map %dx%d >= 5x5, peaks %d <= 16384, humans %d <= 1024)",
-                    max_batch, max_h, max_w, max_peaks, max_humans);
+    if (max_part <= 0) max_part = EKP_MAX_PART;
+    if (max_cand <= 0) max_cand = EKP_MAX_CAND;
+    if (max_batch < 1 || max_batch > 65535 || max_h < 5 || max_w < 5 || max_peaks < 1 || max_humans < 1 || max_peaks > EKP_LIMIT_PEAKS ||
+        max_humans > EKP_LIMIT_HUMANS || max_part < 1 || max_part > EKP_LIMIT_PART || max_cand < 64 || max_cand > EKP_LIMIT_CAND)
+        return fail(EKP_ERR_ARG, "ekp_create: bad capacity (batch %d <= 65535, map %dx%d >= 5x5, peaks %d <= %d, humans %d <= %d, "
+                    "peaks per part %d <= %d, candidates per limb 64 <= %d <= %d)", max_batch, max_h, max_w, max_peaks, EKP_LIMIT_PEAKS,
+                    max_humans, EKP_LIMIT_HUMANS, max_part, EKP_LIMIT_PART, max_cand, EKP_LIMIT_CAND);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -193,7 +226,8 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
     CU(cudaSetDevice(device));
     ekp_ctx* c = new ekp_ctx();
     c->device = device; c->max_batch = max_batch; c->max_h = max_h; c->max_w = max_w;
-    c->max_peaks = max_peaks; c->max_humans = max_humans;
+    c->max_peaks = max_peaks; c->max_humans = max_humans; c->max_part = max_part; c->max_cand = max_cand;
+    c->graphs = new std::vector<GraphEntry>();
     const size_t B = (size_t) max_batch;
 #define DEV_ALLOC(ptr, bytes)                                                     \
     do {                                                                          \
@@ -211,7 +245,7 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
     DEV_ALLOC(c->line, sizeof(ekp_peak) * B * max_peaks);
     DEV_ALLOC(c->part_off, sizeof(int) * B * 20);
     DEV_ALLOC(c->n_peaks, sizeof(int) * B);
-    DEV_ALLOC(c->conns, sizeof(Conn) * B * EKP_NUM_LIMB * EKP_MAX_PART);
+    DEV_ALLOC(c->conns, sizeof(Conn) * B * EKP_NUM_LIMB * max_part);
     DEV_ALLOC(c->n_conns, sizeof(int) * B * EKP_NUM_LIMB);
     c->lay.off_subset = 16;
     c->lay.off_hparts = c->lay.off_subset + sizeof(float) * 20 * (size_t) max_humans;
@@ -232,7 +266,8 @@ extern "C" int ekp_create(ekp_ctx** out, int device, int max_batch, int max_h, i
         e = set_interior_taps(t8.data() + 16 * 8);
     }
     if (e == cudaSuccess) e = configure_peaks_sort(max_peaks);
-    if (e == cudaSuccess) e = configure_assemble(max_humans, max_peaks);
+    if (e == cudaSuccess) e = configure_connect(max_part, max_cand, max_h, max_w);
+    if (e == cudaSuccess) e = configure_assemble(max_humans, max_peaks, max_part);
     if (e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "context setup: %s", cudaGetErrorString(e)); }
     *out = c;
     return EKP_OK;
@@ -243,7 +278,24 @@ extern "C" int ekp_last_batch(const ekp_ctx* c) { return c && c->has_run ? c->la
 extern "C" int ekp_max_batch(const ekp_ctx* c) { return c ? c->max_batch : 0; }
 extern "C" int ekp_max_peaks(const ekp_ctx* c) { return c ? c->max_peaks : 0; }
 extern "C" int ekp_max_humans(const ekp_ctx* c) { return c ? c->max_humans : 0; }
+extern "C" int ekp_max_part(const ekp_ctx* c) { return c ? c->max_part : 0; }
+extern "C" int ekp_max_cand(const ekp_ctx* c) { return c ? c->max_cand : 0; }
 extern "C" long long ekp_kernel_launches(const ekp_ctx* c) { return c ? c->launches : 0; }
+extern "C" long long ekp_graph_launches(const ekp_ctx* c) { return c ? c->graph_launches : 0; }
+
+// Pinned host memory for the host-buffer entry point: one block that holds a batch's heat tensor directly followed by
+// its PAF tensor arrives on the device with ONE copy.  write_combined != 0 asks for write-combined memory (the CPU must
+// only write it, sequentially; reads are uncached and slow).
+extern "C" int ekp_host_alloc(void** out, size_t bytes, int write_combined) {
+    if (!out || bytes == 0) return fail(EKP_ERR_ARG, "ekp_host_alloc: bad arguments");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    return EKP_OK;
+}
+extern "C" int ekp_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return EKP_OK;
+}
 
 static int ensure_tables(ekp_ctx* c, int h, int w, cudaStream_t stream) {
     if (c->tab_h == h && c->tab_w == w) return EKP_OK;
@@ -257,6 +309,9 @@ static int ensure_tables(ekp_ctx* c, int h, int w, cudaStream_t stream) {
                 return fail(EKP_ERR_STATE, "internal: interior taps are not periodic at row %d", Y);
     }
     CU(cudaStreamSynchronize(stream));  // nothing in flight may still read the old tables
+    if (c->has_run) CU(cudaEventSynchronize(c->done));
+    for (GraphEntry& e : *c->graphs) cudaGraphExecDestroy(e.exec);  // captured with the old table pointers
+    c->graphs->clear();
     if (c->ax) { cudaFree(c->ax); c->ax = nullptr; }
     if (c->ay) { cudaFree(c->ay); c->ay = nullptr; }
     c->tab_h = c->tab_w = 0;
@@ -281,20 +336,30 @@ static int check_shape(const ekp_ctx* c, int n, int h, int w, int layout, const 
 // stages 4-5 + result copies, shared by every entry point
 static int run_peak_sort(ekp_ctx* c, int n, int id_from_key, cudaStream_t st) {
     mark(c, 1, st);
-    CU(launch_peaks_sort(c->raw, c->raw_count, c->max_peaks, id_from_key, n, c->line, c->part_off, c->n_peaks, c->overflow, st));
+    CU(launch_peaks_sort(c->raw, c->raw_count, c->max_peaks, c->max_part, id_from_key, n, c->line, c->part_off, c->n_peaks, c->overflow, st));
     c->launches += 1;
     return EKP_OK;
 }
 static int run_connect_assemble(ekp_ctx* c, int n, const PafSource& paf, int h1, cudaStream_t st) {
     mark(c, 2, st);
-    CU(launch_paf_connect(c->line, c->part_off, c->max_peaks, paf, h1, n, c->conns, c->n_conns, c->overflow, st));
+    ConnectParams cp;
+    cp.line = c->line; cp.part_off = c->part_off; cp.max_peaks = c->max_peaks; cp.max_part = c->max_part; cp.max_cand = c->max_cand;
+    cp.paf = paf; cp.h1 = h1; cp.conns = c->conns; cp.n_conns = c->n_conns; cp.overflow = c->overflow;
+    CU(launch_paf_connect(cp, n, st));
     mark(c, 3, st);
-    CU(launch_assemble(c->line, c->max_peaks, c->n_peaks, c->conns, c->n_conns, c->max_humans, n, c->overflow, c->records,
-                       c->lay, st));
+    AsmParams ap;
+    ap.line = c->line; ap.max_peaks = c->max_peaks; ap.n_peaks = c->n_peaks; ap.part_off = c->part_off; ap.conns = c->conns;
+    ap.n_conns = c->n_conns; ap.max_part = c->max_part; ap.max_humans = c->max_humans; ap.conn_cap = 0; ap.overflow = c->overflow;
+    ap.records = c->records; ap.lay = c->lay;
+    CU(launch_assemble(ap, n, st));
     mark(c, 4, st);
     if (c->timing) c->timed_runs++;
     c->launches += 2;
     CU(cudaMemcpyAsync(c->h_records, c->records, c->lay.stride * (size_t) n, cudaMemcpyDeviceToHost, st));  // one packed copy
+    return EKP_OK;
+}
+// after a batch has been put on `st` (eagerly or as a graph launch): results become readable when `done` fires
+static int finish_submit(ekp_ctx* c, int n, cudaStream_t st) {
     CU(cudaEventRecord(c->done, st));
     c->last_stream = st; c->last_n = n; c->has_run = true;
     return EKP_OK;
@@ -305,13 +370,123 @@ static int run_back_half(ekp_ctx* c, int n, int id_from_key, const PafSource& pa
     return run_connect_assemble(c, n, paf, h1, st);
 }
 
+// ---- one batch, stages 1-5 ------------------------------------------------------------------------------------
+// Everything one batch puts on a stream: input copies (host entry), counters, the kernels of stages 1-5 and the one packed
+// device-to-host copy of the result records.  Issued eagerly or into a stream capture; returns the kernels launched.
+static int enqueue_batch(ekp_ctx* c, const PostArgs& a, cudaStream_t st, int* kernels) {
+    int k = 0;
+    if (a.heat_host) {
+        // one copy when the caller's two tensors are adjacent in host memory (one pinned block: heat, then paf), else two
+        if (reinterpret_cast<const char*>(a.heat_host) + a.h2d_heat_bytes == reinterpret_cast<const char*>(a.paf_host) &&
+            reinterpret_cast<const char*>(a.heat) + a.h2d_heat_bytes == reinterpret_cast<const char*>(a.paf)) {
+            CU(cudaMemcpyAsync(const_cast<float*>(a.heat), a.heat_host, a.h2d_heat_bytes + a.h2d_paf_bytes, cudaMemcpyHostToDevice, st));
+        } else {
+            CU(cudaMemcpyAsync(const_cast<float*>(a.heat), a.heat_host, a.h2d_heat_bytes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(const_cast<float*>(a.paf), a.paf_host, a.h2d_paf_bytes, cudaMemcpyHostToDevice, st));
+        }
+    }
+    CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+    PafSource src;
+    src.layout = a.layout; src.H = 8 * a.h; src.W = 8 * a.w; src.C = EKP_PAF_CH; src.h = a.h; src.w = a.w;
+    src.pair_base = nullptr; src.ids_are_rows = 1;
+    if (a.frontend == EKP_FRONTEND_DENSE) {
+        mark(c, 0, st);
+        DenseParams p;
+        p.heat = a.heat; p.paf = a.paf; p.n = a.n; p.h = a.h; p.w = a.w; p.layout = a.layout; p.thr = a.thr;
+        p.ax = c->ax; p.ay = c->ay; p.heat_mat = a.heat_mat; p.paf_mat = a.paf_mat; p.smooth_out = nullptr;
+        p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.tile_wl = dense_frontend_tile_wl(a.w);
+        CU(launch_dense_frontend(p, st));
+        k += 1;
+        // Stage 4 evaluates the bilinear expression of the materialising kernel on the stride-8 PAF (bit-identical to
+        // reading the materialised paf_mat[y][x], tests/test_gpu_parity.py: lean == materialised): the stride-8 planes
+        // are L2- (or shared-memory-) resident, while gathers from the 36 MB-per-image paf_mat go to DRAM.
+        // EKP_CONNECT_FROM_MAT=1 reads paf_mat instead, exactly as the reference's process_paf does.
+        static const bool from_mat = getenv("EKP_CONNECT_FROM_MAT") && atoi(getenv("EKP_CONNECT_FROM_MAT")) != 0;
+        if (a.paf_mat && from_mat) { src.ptr = a.paf_mat; src.mode = PAF_FULL_HWC; }
+        else { src.ptr = a.paf; src.mode = PAF_LO_BILINEAR; }
+    } else {
+        mark(c, 0, st);
+        RefParams p;
+        p.heat = a.heat; p.n = a.n; p.h = a.h; p.w = a.w; p.layout = a.layout; p.thr = a.thr;
+        p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.cubic = c->cubic;
+        p.refine = a.frontend == EKP_FRONTEND_REFERENCE ? 1 : 0;
+        CU(launch_ref_frontend(p, st));
+        k += 1;
+        if (a.paf_mat) { CU(launch_upsample_nearest(a.paf, a.layout, a.n, a.h, a.w, EKP_PAF_CH, a.paf_mat, st)); k += 1; }
+        if (a.heat_mat) { CU(launch_upsample_nearest(a.heat, a.layout, a.n, a.h, a.w, EKP_HEAT_CH, a.heat_mat, st)); k += 1; }
+        src.ptr = a.paf; src.mode = PAF_LO_NEAREST;  // == paf_mat[y][x] exactly (cv2 INTER_NEAREST x8)
+    }
+    const long long before = c->launches;
+    int rc = run_back_half(c, a.n, /*id_from_key=*/0, src, /*h1=*/8 * a.h, st);
+    if (rc) return rc;
+    k += (int) (c->launches - before);
+    c->launches = before;  // the caller accounts for the whole batch
+    *kernels = k;
+    return EKP_OK;
+}
+
+// A batch with the same pointers, shape and flags as an earlier one (a stream of frames through the same buffers)
+// is replayed as a CUDA graph: one launch call instead of nine stream operations, and no gaps between the small
+// latency-bound kernels of stages 4-5.  EKP_GRAPHS=0 keeps everything eager (as does per-stage timing).
+static const size_t kMaxGraphs = 8;
+
+static int submit_batch(ekp_ctx* c, const PostArgs& a, cudaStream_t st) {
+    if (c->has_run && c->last_stream != st) CU(cudaStreamWaitEvent(st, c->done, 0));  // the work buffers are per context
+    int kernels = 0;
+    static const bool graphs_off = getenv("EKP_GRAPHS") && atoi(getenv("EKP_GRAPHS")) == 0;
+    const bool use_graph = !graphs_off && !c->timing && c->graphs_ok;
+    if (!use_graph) {
+        int rc = enqueue_batch(c, a, st, &kernels);
+        if (rc) return rc;
+        c->launches += kernels;
+    } else {
+        std::vector<GraphEntry>& G = *c->graphs;
+        GraphEntry* hit = nullptr;
+        for (GraphEntry& e : G) if (same_args(e.key, a)) hit = &e;
+        if (!hit) {
+            if (!c->cap_stream) CU(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_batch(c, a, c->cap_stream, &kernels);
+            cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc == EKP_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != EKP_OK || ce != cudaSuccess || !exec) {  // no graph on this driver / for this sequence: stay eager from now on
+                cudaGetLastError();
+                c->graphs_ok = false;
+                return submit_batch(c, a, st);
+            }
+            if (G.size() >= kMaxGraphs) {  // evict the least recently used
+                size_t lru = 0;
+                for (size_t i = 1; i < G.size(); i++) if (G[i].stamp < G[lru].stamp) lru = i;
+                cudaGraphExecDestroy(G[lru].exec);
+                G.erase(G.begin() + (long) lru);
+            }
+            G.push_back(GraphEntry{a, exec, kernels, 0});
+            hit = &G.back();
+        }
+        hit->stamp = ++c->graph_clock;
+        CU(cudaGraphLaunch(hit->exec, st));
+        c->launches += hit->kernels;
+        c->graph_launches += 1;
+    }
+    return finish_submit(c, a.n, st);
+}
+
+static int check_post_args(const ekp_ctx* c, int n, int h, int w, int layout, int frontend, const char* who) {
+    int rc = check_shape(c, n, h, w, layout, who);
+    if (rc) return rc;
+    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE && frontend != EKP_FRONTEND_REFERENCE_COARSE)
+        return fail(EKP_ERR_ARG, "%s: frontend %d", who, frontend);
+    return EKP_OK;
+}
+
 extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, int n, int h, int w, int layout,
                                float thr_heat, int frontend, float* heat_mat, float* paf_mat, void* stream) {
-    int rc = check_shape(c, n, h, w, layout, "ekp_postprocess");
+    int rc = check_post_args(c, n, h, w, layout, frontend, "ekp_postprocess");
     if (rc) return rc;
     if (!heat || !paf) return fail(EKP_ERR_ARG, "ekp_postprocess: NULL input");
-    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE && frontend != EKP_FRONTEND_REFERENCE_COARSE)
-        return fail(EKP_ERR_ARG, "ekp_postprocess: frontend %d", frontend);
     if (heat_mat && !paf_mat) return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat without paf_mat");
     if ((reinterpret_cast<uintptr_t>(heat_mat) | reinterpret_cast<uintptr_t>(paf_mat)) & 15u)
         return fail(EKP_ERR_ARG, "ekp_postprocess: heat_mat / paf_mat must be 16-byte aligned (they are written with 16-byte bulk copies)");
@@ -319,56 +494,33 @@ extern "C" int ekp_postprocess(ekp_ctx* c, const float* heat, const float* paf, 
         return fail(EKP_ERR_ARG, "ekp_postprocess: heat / paf must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t) stream;
     CU(cudaSetDevice(c->device));
-    CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
-    PafSource src;
-    src.layout = layout; src.H = 8 * h; src.W = 8 * w; src.C = EKP_PAF_CH; src.h = h; src.w = w;
-    src.pair_base = nullptr; src.ids_are_rows = 1;
     if (frontend == EKP_FRONTEND_DENSE) {
         rc = ensure_tables(c, h, w, st);
         if (rc) return rc;
-        mark(c, 0, st);
-        DenseParams p;
-        p.heat = heat; p.paf = paf; p.n = n; p.h = h; p.w = w; p.layout = layout; p.thr = thr_heat;
-        p.ax = c->ax; p.ay = c->ay; p.heat_mat = heat_mat; p.paf_mat = paf_mat; p.smooth_out = nullptr;
-        p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.tile_wl = dense_frontend_tile_wl(w);
-        CU(launch_dense_frontend(p, st));
-        c->launches += 1;
-        // Stage 4 reads paf_mat exactly as the reference's process_paf does when it was materialised
-        // (2 loads per sample), else evaluates the same bilinear expression on the stride-8 PAF
-        // (8 loads per sample, bit-identical values: tests/test_gpu_parity.py).
-        if (paf_mat) { src.ptr = paf_mat; src.mode = PAF_FULL_HWC; }
-        else { src.ptr = paf; src.mode = PAF_LO_BILINEAR; }
-    } else {
-        mark(c, 0, st);
-        RefParams p;
-        p.heat = heat; p.n = n; p.h = h; p.w = w; p.layout = layout; p.thr = thr_heat;
-        p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.cubic = c->cubic;
-        p.refine = frontend == EKP_FRONTEND_REFERENCE ? 1 : 0;
-        CU(launch_ref_frontend(p, st));
-        c->launches += 1;
-        if (paf_mat) { CU(launch_upsample_nearest(paf, layout, n, h, w, EKP_PAF_CH, paf_mat, st)); c->launches += 1; }
-        if (heat_mat) { CU(launch_upsample_nearest(heat, layout, n, h, w, EKP_HEAT_CH, heat_mat, st)); c->launches += 1; }
-        src.ptr = paf; src.mode = PAF_LO_NEAREST;  // == paf_mat[y][x] exactly (cv2 INTER_NEAREST x8)
     }
-    return run_back_half(c, n, /*id_from_key=*/0, src, /*h1=*/8 * h, st);
+    PostArgs a = {};
+    a.heat = heat; a.paf = paf; a.n = n; a.h = h; a.w = w; a.layout = layout; a.frontend = frontend; a.thr = thr_heat;
+    a.heat_mat = heat_mat; a.paf_mat = paf_mat;
+    return submit_batch(c, a, st);
 }
 
 extern "C" int ekp_postprocess_host(ekp_ctx* c, const float* heat_host, const float* paf_host, int n, int h, int w,
                                     int layout, float thr_heat, int frontend, int materialize, void* stream) {
-    int rc = check_shape(c, n, h, w, layout, "ekp_postprocess_host");
+    int rc = check_post_args(c, n, h, w, layout, frontend, "ekp_postprocess_host");
     if (rc) return rc;
     if (!heat_host || !paf_host) return fail(EKP_ERR_ARG, "ekp_postprocess_host: NULL input");
     cudaStream_t st = (cudaStream_t) stream;
     CU(cudaSetDevice(c->device));
-    if (!c->in_heat) {
-        CU(cudaMalloc((void**) &c->in_heat, sizeof(float) * (size_t) c->max_batch * c->max_h * c->max_w * EKP_HEAT_CH));
-        CU(cudaMalloc((void**) &c->in_paf, sizeof(float) * (size_t) c->max_batch * c->max_h * c->max_w * EKP_PAF_CH));
-    }
+    if (!c->in_block)  // ONE staging block: heat, directly followed by paf (so adjacent host tensors arrive with one copy)
+        CU(cudaMalloc((void**) &c->in_block, sizeof(float) * (size_t) c->max_batch * c->max_h * c->max_w * (EKP_HEAT_CH + EKP_PAF_CH)));
     const size_t hw = (size_t) h * w;
     float *hm = nullptr, *pm = nullptr;
     if (materialize) {
         if (c->mat_images < (size_t) n || c->mat_hw < hw) {
             CU(cudaStreamSynchronize(st));
+            if (c->has_run) CU(cudaEventSynchronize(c->done));
+            for (GraphEntry& e : *c->graphs) cudaGraphExecDestroy(e.exec);  // they point at the old tensors
+            c->graphs->clear();
             if (c->mat_heat) { cudaFree(c->mat_heat); c->mat_heat = nullptr; }
             if (c->mat_paf) { cudaFree(c->mat_paf); c->mat_paf = nullptr; }
             c->mat_images = 0; c->mat_hw = 0;
@@ -379,9 +531,17 @@ extern "C" int ekp_postprocess_host(ekp_ctx* c, const float* heat_host, const fl
         }
         hm = c->mat_heat; pm = c->mat_paf;
     }
-    CU(cudaMemcpyAsync(c->in_heat, heat_host, sizeof(float) * (size_t) n * hw * EKP_HEAT_CH, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->in_paf, paf_host, sizeof(float) * (size_t) n * hw * EKP_PAF_CH, cudaMemcpyHostToDevice, st));
-    return ekp_postprocess(c, c->in_heat, c->in_paf, n, h, w, layout, thr_heat, frontend, hm, pm, stream);
+    if (frontend == EKP_FRONTEND_DENSE) {
+        rc = ensure_tables(c, h, w, st);
+        if (rc) return rc;
+    }
+    PostArgs a = {};
+    a.heat_host = heat_host; a.paf_host = paf_host;
+    a.h2d_heat_bytes = sizeof(float) * (size_t) n * hw * EKP_HEAT_CH;
+    a.h2d_paf_bytes = sizeof(float) * (size_t) n * hw * EKP_PAF_CH;
+    a.heat = c->in_block; a.paf = c->in_block + (size_t) n * hw * EKP_HEAT_CH;
+    a.n = n; a.h = h; a.w = w; a.layout = layout; a.frontend = frontend; a.thr = thr_heat; a.heat_mat = hm; a.paf_mat = pm;
+    return submit_batch(c, a, st);
 }
 
 extern "C" int ekp_process_paf_dev(ekp_ctx* c, const float* peaks, const int* n_peaks, int peaks_stride, int n, int h1,
@@ -392,6 +552,7 @@ extern "C" int ekp_process_paf_dev(ekp_ctx* c, const float* peaks, const int* n_
     if (H < 1 || W < 1 || C < 38 || peaks_stride < 1) return fail(EKP_ERR_ARG, "ekp_process_paf_dev: bad dims H=%d W=%d C=%d (C >= 38)", H, W, C);
     cudaStream_t st = (cudaStream_t) stream;
     CU(cudaSetDevice(c->device));
+    if (c->has_run && c->last_stream != st) CU(cudaStreamWaitEvent(st, c->done, 0));
     CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
     mark(c, 0, st);
     CU(launch_peaks_ingest(peaks, n_peaks, 0, peaks_stride, 5, n, W, H, c->raw, c->raw_count, c->max_peaks, c->overflow, st));
@@ -399,7 +560,9 @@ extern "C" int ekp_process_paf_dev(ekp_ctx* c, const float* peaks, const int* n_
     PafSource src;
     src.ptr = paf_mat; src.mode = PAF_FULL_HWC; src.layout = EKP_LAYOUT_NHWC; src.H = H; src.W = W; src.C = C; src.h = H / 8; src.w = W / 8;
     src.pair_base = nullptr; src.ids_are_rows = 0;
-    return run_back_half(c, n, /*id_from_key=*/1, src, h1, st);
+    int rc = run_back_half(c, n, /*id_from_key=*/1, src, h1, st);
+    if (rc) return rc;
+    return finish_submit(c, n, st);
 }
 
 static int wait_results(ekp_ctx* c, const char* who) {
@@ -417,7 +580,7 @@ static int overflow_status(const ekp_ctx* c) {
     for (int i = 0; i < c->last_n; i++) any |= rec_head(c, i)->overflow;
     if (any & EKP_OVF_BADPEAK) return fail(EKP_ERR_ARG, "a peak has part id outside [0,18), coordinates outside the PAF map, or a NaN score");
     if (any) return fail(EKP_ERR_CAPACITY, "capacity overflow (bits 0x%x: 1 peaks>%d, 2 part>%d, 4 candidates>%d, 8 humans>%d)", any,
-                         c->max_peaks, EKP_MAX_PART, EKP_MAX_CAND, c->max_humans);
+                         c->max_peaks, c->max_part, c->max_cand, c->max_humans);
     return EKP_OK;
 }
 
@@ -464,8 +627,10 @@ extern "C" int ekp_debug_std_sort(ekp_ctx* c, float* scores_dev, unsigned* tags_
     if (!c || n < 0 || (n > 0 && (!scores_dev || !tags_dev))) return fail(EKP_ERR_ARG, "ekp_debug_std_sort: bad arguments");
     if (n == 0) return EKP_OK;
     if (n > 16384) return fail(EKP_ERR_ARG, "ekp_debug_std_sort: n %d > 16384", n);
+    if (debug_std_sort_scratch_words(n) * sizeof(unsigned) > sizeof(Conn) * (size_t) c->max_batch * EKP_NUM_LIMB * c->max_part)
+        return fail(EKP_ERR_ARG, "ekp_debug_std_sort: n %d needs more scratch than this context's connection buffer holds", n);
     CU(cudaSetDevice(c->device));
-    // scratch for the replay's range list: the connection buffer (>= 19 * 256 * 16 bytes, idle between runs)
+    // scratch for the replay's work lists: the connection buffer (idle between runs)
     CU(launch_debug_std_sort(scores_dev, tags_dev, n, reinterpret_cast<unsigned*>(c->conns), (cudaStream_t) stream));
     c->launches += 1;
     return EKP_OK;
@@ -609,15 +774,26 @@ std::vector<float> g_hscore;      // [num_humans] subset[18] / subset[19], compu
 std::vector<ekp_peak> g_line;     // part-sorted peak table
 int g_num_humans = 0;
 
-int compat_ctx(int need_peaks, int need_humans) {
-    if (g_ctx && g_ctx->max_peaks >= need_peaks && g_ctx->max_humans >= need_humans) return EKP_OK;
+// The context behind the operator surface: re-created with larger capacities when a scene needs them (the new one
+// first, so a failed creation leaves the old one in place), never beyond the library's limits.
+int compat_ctx(int need_peaks, int need_humans, int need_part, int need_cand) {
+    if (g_ctx && g_ctx->max_peaks >= need_peaks && g_ctx->max_humans >= need_humans && g_ctx->max_part >= need_part &&
+        g_ctx->max_cand >= need_cand)
+        return EKP_OK;
     int dev = 0;
     if (const char* s = getenv("EKP_DEVICE")) dev = atoi(s);
     int peaks = 1024, humans = 128;
     while (peaks < need_peaks) peaks *= 2;
     while (humans < need_humans) humans *= 2;
-    if (g_ctx) { ekp_destroy(g_ctx); g_ctx = nullptr; }
-    return ekp_create(&g_ctx, dev, 1, 8, 8, peaks, humans);
+    peaks = std::min(peaks, EKP_LIMIT_PEAKS);
+    humans = std::min(humans, EKP_LIMIT_HUMANS);
+    if (g_ctx) { need_part = std::max(need_part, g_ctx->max_part); need_cand = std::max(need_cand, g_ctx->max_cand); }
+    ekp_ctx* fresh = nullptr;
+    int rc = ekp_create_ex(&fresh, dev, 1, 8, 8, peaks, humans, std::min(need_part, EKP_LIMIT_PART), std::min(need_cand, EKP_LIMIT_CAND));
+    if (rc) return rc;
+    if (g_ctx) ekp_destroy(g_ctx);
+    g_ctx = fresh;
+    return EKP_OK;
 }
 }  // namespace
 
@@ -629,11 +805,11 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
     if (p1 < 0 || p2 < 0 || p3 < 5 || f1 < 1 || f2 < 1 || f3 < 38 || !pafmap || (!peaks && (long long) p1 * p2 > 0))
         return fail(EKP_ERR_ARG, "process_paf: bad arguments (peaks [%d,%d,%d] needs p3 >= 5, paf [%d,%d,%d] needs f3 >= 38)", p1, p2, p3, f1, f2, f3);
     const long long npk = (long long) p1 * p2;  // all p1 "images" are pooled (pafprocess.cpp:26-36)
-    if (npk > 16384) return fail(EKP_ERR_CAPACITY, "process_paf: %lld peaks > 16384", npk);
+    if (npk > EKP_LIMIT_PEAKS) return fail(EKP_ERR_CAPACITY, "process_paf: %lld peaks > %d", npk, EKP_LIMIT_PEAKS);
     if (npk == 0) return EKP_OK;  // nothing to connect: zero humans, like the reference
-    int need_humans = 128;
-    for (int attempt = 0; attempt < 5; attempt++) {
-        int rc = compat_ctx((int) npk, need_humans);
+    int need_humans = 128, need_part = EKP_MAX_PART, need_cand = EKP_MAX_CAND;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int rc = compat_ctx((int) npk, need_humans, need_part, need_cand);
         if (rc) return rc;
         ekp_ctx* c = g_ctx;
         CU(cudaSetDevice(c->device));
@@ -660,7 +836,7 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
             long long acc = 0;
             for (int l = 0; l < EKP_NUM_LIMB; l++) {
                 pair_base[l] = (int) acc;
-                acc += (long long) std::min(per_part[pairs[l][0]], EKP_MAX_PART) * std::min(per_part[pairs[l][1]], EKP_MAX_PART);
+                acc += (long long) std::min(per_part[pairs[l][0]], c->max_part) * std::min(per_part[pairs[l][1]], c->max_part);
             }
             pair_base[EKP_NUM_LIMB] = (int) acc;
             nsamples = acc * 10;
@@ -693,7 +869,7 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
             if (!g_dev_pair_base) CU(cudaMalloc((void**) &g_dev_pair_base, sizeof(int) * (EKP_NUM_LIMB + 1)));
             CU(cudaMemcpyAsync(g_dev_pair_base, pair_base, sizeof(pair_base), cudaMemcpyHostToDevice, st));
             CU(cudaMemsetAsync(g_dev_offs, 0, (size_t) nsamples * sizeof(unsigned), st));  // limbs the kernel skips stay in bounds
-            CU(launch_pair_sample_offsets(c->line, c->part_off, g_dev_pair_base, f1, f2, f3, g_dev_offs, st));
+            CU(launch_pair_sample_offsets(c->line, c->part_off, g_dev_pair_base, f1, f2, f3, c->max_part, g_dev_offs, st));
             c->launches += 1;
             CU(cudaMemcpyAsync(g_host_offs, g_dev_offs, (size_t) nsamples * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -711,12 +887,21 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
         }
         rc = run_connect_assemble(c, 1, src, h1, st);
         if (rc) return rc;
+        rc = finish_submit(c, 1, st);
+        if (rc) return rc;
         std::vector<ekp_peak> line((size_t) c->max_peaks);
         std::vector<float> subset((size_t) c->max_humans * 20);
         int nh = 0, np = 0;
         unsigned ovf = 0;
         rc = ekp_results(c, &nh, subset.data(), &np, line.data(), &ovf);
-        if (rc == EKP_ERR_CAPACITY && ovf == EKP_OVF_HUMANS && need_humans < 2048) { need_humans *= 4; continue; }
+        if (rc == EKP_ERR_CAPACITY && !(ovf & (EKP_OVF_PEAKS | EKP_OVF_BADPEAK))) {
+            // grow exactly what overflowed, within the library's limits, and run again; at a limit the error stands
+            bool grew = false, stuck = false;
+            if (ovf & EKP_OVF_HUMANS) { if (c->max_humans < EKP_LIMIT_HUMANS) { need_humans = std::min(c->max_humans * 4, EKP_LIMIT_HUMANS); grew = true; } else stuck = true; }
+            if (ovf & EKP_OVF_PART) { if (c->max_part < EKP_LIMIT_PART) { need_part = std::min(c->max_part * 4, EKP_LIMIT_PART); grew = true; } else stuck = true; }
+            if (ovf & EKP_OVF_CANDIDATES) { if (c->max_cand < EKP_LIMIT_CAND) { need_cand = std::min(c->max_cand * 4, EKP_LIMIT_CAND); grew = true; } else stuck = true; }
+            if (grew && !stuck) continue;
+        }
         if (rc) return rc;
         g_num_humans = nh;
         g_subset.assign(subset.begin(), subset.begin() + (size_t) nh * 20);
@@ -725,7 +910,7 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
         g_line.assign(line.begin(), line.begin() + np);
         return EKP_OK;  // the reference returns 0 (pafprocess.cpp:193)
     }
-    return fail(EKP_ERR_CAPACITY, "process_paf: more than 2048 subset rows");
+    return fail(EKP_ERR_CAPACITY, "process_paf: the scene does not fit the library's limits");
 }
 
 extern "C" int get_num_humans(void) { return g_num_humans; }

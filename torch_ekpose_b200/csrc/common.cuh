@@ -95,6 +95,33 @@ inline cudaError_t raise_dynamic_smem_limit(Kernel kernel, size_t bytes) {
 }
 
 // launch parameter blocks --------------------------------------------------------------------
+struct AsmParams {
+    const ekp_peak* line;      // [n][max_peaks] part-sorted peak table
+    int max_peaks;
+    const int* n_peaks;        // [n]
+    const int* part_off;       // [n][20] ([19] = number of raw peaks, the bound of every id)
+    const Conn* conns;         // [n][19][max_part]
+    const int* n_conns;        // [n][19]
+    int max_part, max_humans;
+    int conn_cap;              // staged connection records per image (set by launch_assemble)
+    const unsigned* overflow;  // [n]
+    unsigned char* records;    // [n] packed result records
+    ResultLayout lay;
+};
+
+struct ConnectParams {
+    const ekp_peak* line;
+    const int* part_off;
+    int max_peaks, max_part, max_cand;
+    PafSource paf;
+    int h1;
+    int stage_min_pairs;       // a block stages the limb's planes in shared memory when it has at least this many pairs
+    int by_sample_max_pairs;   // ... and scores with ten lanes per pair when it has at most this many (else one thread per pair)
+    Conn* conns;               // [n][19][max_part]
+    int* n_conns;              // [n][19]
+    unsigned* overflow;
+};
+
 struct DenseParams {
     const float* heat;
     const float* paf;

@@ -22,6 +22,8 @@
 //    n > 16 AND ties exist does one warp replay libstdc++'s algorithm on the original sequence
 //    (introsort: median-of-3 quicksort above 16 elements, heapsort after 2*floor(log2 n) levels,
 //    then the final insertion sort), which reproduces the reference's permutation exactly.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ekp {
@@ -30,7 +32,16 @@ namespace ekp {
 #define EKP_CONN_THREADS 128
 #endif
 constexpr int kConnThreads = EKP_CONN_THREADS;
-constexpr int kSurvWindow = 2048;  // pairs per pass-1 window (survivor list capacity)
+constexpr int kMaxPartLimit = 1024;  // upper bound of the per-context max_part (bitmaps of used peaks are static)
+
+// where stage 4 reads the PAF from
+enum ConnSrc {
+    SRC_GLOBAL = 0,       // gathers from global memory, one load per channel
+    SRC_GLOBAL_VEC2 = 1,  // channel-last tensor: both channels of a limb with one 8-byte load
+    SRC_SMEM_PLANES = 2   // the limb's two stride-8 planes staged in shared memory (NCHW network output): the gathers,
+                          // which bound this kernel through the L1 tag rate (one tag per lane per divergent load:
+                          // 23.8 M tags = the whole 80 us of the crowded batch, profiles/README.md), become shared-memory reads
+};
 
 struct Sample2 { float x, y; };
 
@@ -50,10 +61,48 @@ __device__ __forceinline__ Sample2 pair_at(const float* q, int ch1, int ch2) {
     return r;
 }
 
+// The limb's two stride-8 planes (channels ch1, ch1 + 1 of an NCHW tensor: adjacent in memory) interleaved
+// as float2 in shared memory, coalesced (16-byte loads when the planes allow it).
+template <int kT>
+__device__ __forceinline__ void stage_planes(float2* __restrict__ sP, const PafSource& s, int img, int ch1) {
+    const int hw = s.h * s.w;
+    const float* p1 = s.ptr + ((size_t) img * s.C + ch1) * hw;
+    const float* p2 = p1 + hw;
+    if ((hw & 3) == 0 && (reinterpret_cast<uintptr_t>(p1) & 15) == 0) {
+        float4* d = reinterpret_cast<float4*>(sP);
+        for (int i = threadIdx.x; i < (hw >> 2); i += kT) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p1) + i), b = __ldg(reinterpret_cast<const float4*>(p2) + i);
+            d[2 * i] = make_float4(a.x, b.x, a.y, b.y);
+            d[2 * i + 1] = make_float4(a.z, b.z, a.w, b.w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < hw; i += kT) sP[i] = make_float2(__ldg(p1 + i), __ldg(p2 + i));
+    }
+}
+
 // `packed` = index of this sample in the pre-gathered list (PAF_PACKED only)
-template <bool kVec2>
-__device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int ly, int lx, int ch1, int ch2, long long packed) {
+template <int kSrc>
+__device__ __forceinline__ Sample2 paf_sample(const PafSource& s, const float2* __restrict__ sP, int img, int ly, int lx, int ch1,
+                                              int ch2, long long packed) {
+    constexpr bool kVec2 = kSrc == SRC_GLOBAL_VEC2;
     Sample2 r;
+    if (kSrc == SRC_SMEM_PLANES) {  // same values, same arithmetic as the global paths below
+        lx = min(max(lx, 0), s.W - 1);
+        ly = min(max(ly, 0), s.H - 1);
+        if (s.mode == PAF_LO_NEAREST) {
+            const float2 v = sP[(ly >> 3) * s.w + (lx >> 3)];
+            r.x = v.x; r.y = v.y;
+        } else {
+            int i0, i1, j0, j1;
+            float tx, ty;
+            bilin_coord(lx, s.w, i0, i1, tx);
+            bilin_coord(ly, s.h, j0, j1, ty);
+            const float2 c00 = sP[j0 * s.w + i0], c01 = sP[j0 * s.w + i1], c10 = sP[j1 * s.w + i0], c11 = sP[j1 * s.w + i1];
+            r.x = lerp1(lerp1(c00.x, c01.x, tx), lerp1(c10.x, c11.x, tx), ty);
+            r.y = lerp1(lerp1(c00.y, c01.y, tx), lerp1(c10.y, c11.y, tx), ty);
+        }
+        return r;
+    }
     if (s.mode == PAF_PACKED) {
         const float2 v = __ldg(reinterpret_cast<const float2*>(s.ptr) + packed);
         r.x = v.x; r.y = v.y;
@@ -96,9 +145,9 @@ __device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int l
 // Pass 1: can the pair still satisfy criterion1 > 6 (pafprocess.cpp:80,85)?  Evaluates samples 3..6 with the
 // float operations of score_pair; false when all four are <= 0.05 (then at most 6 of 10 can pass) or the
 // two peaks coincide (:66).
-template <bool kVec2>
-__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1, int ch2,
-                                              long long packed0) {
+template <int kSrc>
+__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, const float2* __restrict__ sP,
+                                              int img, int ch1, int ch2, long long packed0) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
     float vx = (float) dxi, vy = (float) dyi;
     const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
@@ -113,7 +162,7 @@ __device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak&
         const int i = 3 + k;
         const int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);
         const int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
-        sv[k] = paf_sample<kVec2>(paf, img, ly, lx, ch1, ch2, packed0 + i);
+        sv[k] = paf_sample<kSrc>(paf, sP, img, ly, lx, ch1, ch2, packed0 + i);
     }
     bool any = false;
 #pragma unroll
@@ -122,9 +171,9 @@ __device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak&
 }
 
 // pafprocess.cpp:59-94 for one (a, b) pair.  Returns true when the pair becomes a candidate.
-template <bool kVec2>
-__device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1,
-                                           int ch2, int h1, float& criterion2, long long packed0) {
+template <int kSrc>
+__device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, const float2* __restrict__ sP,
+                                           int img, int ch1, int ch2, int h1, float& criterion2, long long packed0) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
     float vx = (float) dxi, vy = (float) dyi;
     const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
@@ -141,7 +190,7 @@ __device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b,
     }
     Sample2 sv[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kVec2>(paf, img, ly[i], lx[i], ch1, ch2, packed0 + i);  // independent gathers in flight
+    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kSrc>(paf, sP, img, ly[i], lx[i], ch1, ch2, packed0 + i);  // independent gathers in flight
     float scores = 0.0f;
     int criterion1 = 0;
 #pragma unroll
@@ -209,10 +258,10 @@ __device__ void sort_heapsort(const CandArray& A, int first, int last) {  // __p
         sort_adjust_heap(A, first, 0, last - first, value);
     }
 }
-// ---- the same algorithm executed by ONE WARP ---------------------------------------------------
+// ---- the same algorithm, one range per WARP ------------------------------------------------------
 // Control flow, comparisons and element moves of the quicksort phase are exactly libstdc++'s (same
 // order), but every scan ("advance while comp holds") inspects 32 elements per step with a ballot; the
-// final insertion sort runs one lane per independent range (see std_sort_desc).  All 32 lanes call
+// final insertion sort runs one thread per independent range (see std_sort_desc_block).  All 32 lanes call
 // these with identical arguments.
 __device__ __forceinline__ int lead_true(unsigned m) { return m == 0xffffffffu ? 32 : __ffs(~m) - 1; }
 
@@ -247,91 +296,160 @@ __device__ int warp_partition(const CandArray& A, int lo, int hi, float pivot, i
 // stops the right scan, and no position is examined again after its swap.  So the stoppers of both windows are found
 // with two ballots on the original values, the first min(nl, nr) pairs are swapped by one lane each, and the fronts
 // move exactly where the sequential scan would stand: past a window whose stoppers are used up, or ON the first unused
-// stopper of the other (it waits for a partner from the next window).  Returns with hi - lo < 64; the caller finishes
-// with warp_partition.
+// stopper of the other (it waits for a partner from the next window).  The windows shrink with the gap (32, 16, 8
+// elements); returns with hi - lo < 16 and the caller finishes with warp_partition.
 __device__ void warp_partition_wide(const CandArray& A, int& lo, int& hi, float pivot) {
     const int lane = threadIdx.x & 31;
-    while (hi - lo >= 64) {
-        const unsigned stopL = __ballot_sync(0xffffffffu, !(A.s[lo + lane] > pivot));       // comp(first, pivot) fails
-        const unsigned stopR = __ballot_sync(0xffffffffu, !(pivot > A.s[hi - 32 + lane]));  // comp(pivot, last) fails
+    while (hi - lo >= 16) {
+        // two disjoint windows of W elements at the fronts (the argument above holds for any W with hi - lo >= 2 W)
+        const int W = hi - lo >= 64 ? 32 : (hi - lo >= 32 ? 16 : 8);
+        const bool in = lane < W;
+        const unsigned stopL = __ballot_sync(0xffffffffu, in && !(A.s[lo + lane] > pivot));      // comp(first, pivot) fails
+        const unsigned stopR = __ballot_sync(0xffffffffu, in && !(pivot > A.s[hi - W + lane]));  // comp(pivot, last) fails
         const int nl = __popc(stopL), nr = __popc(stopR);
         const int pairs = min(nl, nr);
         if (lane < pairs) {
-            const int i = lo + (int) __fns(stopL, 0, lane + 1);           // lane-th stopper from the left
-            const int j = hi - 32 + (int) __fns(stopR, 31, -(lane + 1));  // lane-th stopper from the right
+            const int i = lo + (int) __fns(stopL, 0, lane + 1);          // lane-th stopper from the left
+            const int j = hi - W + (int) __fns(stopR, 31, -(lane + 1));  // lane-th stopper from the right
             A.swap(i, j);
         }
         __syncwarp();
         const int lo0 = lo, hi0 = hi;
-        lo = nl > pairs ? lo0 + (int) __fns(stopL, 0, pairs + 1) : lo0 + 32;
-        hi = nr > pairs ? hi0 - 32 + (int) __fns(stopR, 31, -(pairs + 1)) + 1 : hi0 - 32;
+        lo = nl > pairs ? lo0 + (int) __fns(stopL, 0, pairs + 1) : lo0 + W;
+        hi = nr > pairs ? hi0 - W + (int) __fns(stopR, 31, -(pairs + 1)) + 1 : hi0 - W;
     }
 }
 
-__device__ void std_sort_desc(const CandArray& A, int n, unsigned* blocks) {
+// ---- ... and by ALL WARPS of the block -----------------------------------------------------------------
+// __introsort_loop only ever recurses into disjoint ranges, so the order in which the ranges are finished does not
+// change the result: the ranges still to be partitioned sit in an append-only queue, every warp takes the next
+// ticket, partitions its range (pushing the right part, keeping the left, like the sequential loop), and ranges of
+// <= 16 elements go to the list of the final insertion sort.  The critical path is one root-to-leaf chain of
+// partitions (n + n/2 + n/4 ...) instead of all of them one after the other.
+struct ReplayWork {
+    unsigned* range;   // queue: (first << 16 | last), 0 = not published yet; n <= 65535
+    unsigned* depth;   // queue: depth limit left for that range
+    int cap;           // queue entries (>= pushes + number of warps)
+    unsigned* blocks;  // [n] per element: the range (packed like `range`) the final insertion sort handles it in, 0 = none
+    int* ctl;          // [4]: head (next ticket), tail (next free entry), pending (ranges pushed and not finished)
+};
+
+// a range of 2..16 elements the quicksort leaves to the final insertion sort: every element learns its range
+__device__ __forceinline__ void replay_add_block(const ReplayWork& W, int first, int last) {
+    const int lane = threadIdx.x & 31;
+    if (lane < last - first) W.blocks[first + lane] = ((unsigned) first << 16) | (unsigned) last;
+}
+__device__ __forceinline__ void replay_push(const ReplayWork& W, int first, int last, int depth) {
+    __threadfence_block();  // this warp's swaps inside [first, last) before the range is published
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&W.ctl[2], 1);
+        const int t = atomicAdd(&W.ctl[1], 1);
+        W.depth[t] = (unsigned) depth;
+        __threadfence_block();
+        reinterpret_cast<volatile unsigned*>(W.range)[t] = ((unsigned) first << 16) | (unsigned) last;
+    }
+}
+
+// one range of the introsort loop, by one warp (all 32 lanes call this with identical arguments)
+__device__ void replay_range(const CandArray& A, int n, int first, int last, int depth, const ReplayWork& W) {
+    const int lane = threadIdx.x & 31;
+    while (last - first > 16) {
+        if (depth == 0) {  // heapsort fallback: never reached by real scenes, kept serial
+            if (lane == 0) sort_heapsort(A, first, last);
+            __syncwarp();
+            return;
+        }
+        --depth;
+        const int mid = first + (last - first) / 2;
+        if (lane == 0) {  // __move_median_to_first(first, first+1, mid, last-1)
+            const int a = first + 1, b = mid, c = last - 1;
+            if (A.comp(a, b)) {
+                if (A.comp(b, c)) A.swap(first, b);
+                else if (A.comp(a, c)) A.swap(first, c);
+                else A.swap(first, a);
+            } else if (A.comp(a, c)) A.swap(first, a);
+            else if (A.comp(b, c)) A.swap(first, c);
+            else A.swap(first, b);
+        }
+        __syncwarp();
+        int plo = first + 1, phi = last;
+        const float pivot = A.s[first];
+        warp_partition_wide(A, plo, phi, pivot);
+        const int cut = warp_partition(A, plo, phi, pivot, n);
+        if (last - cut > 16) replay_push(W, cut, last, depth);   // __introsort_loop(cut, last, depth)
+        else if (last - cut > 1) replay_add_block(W, cut, last);
+        last = cut;
+    }
+    if (last - first > 1) replay_add_block(W, first, last);  // a range the quicksort leaves to the final insertion sort
+}
+
+// Called by every thread of the block (blockDim.x a multiple of 32); A may live in shared or global memory.
+__device__ void std_sort_desc_block(const CandArray& A, int n, const ReplayWork& W) {
     if (n <= 0) return;
     const int lane = threadIdx.x & 31;
-    // __introsort_loop with an explicit stack: the recursion only ever touches disjoint ranges,
-    // so the order in which they are finished does not change the result.
-    int stk_first[48], stk_last[48], stk_depth[48];
-    int sp = 0, nblk = 0;
-    int lg = 0;
-    for (int v = n; v > 1; v >>= 1) lg++;
-    stk_first[sp] = 0; stk_last[sp] = n; stk_depth[sp] = 2 * lg; sp++;
-    while (sp) {
-        --sp;
-        int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
-        bool heapsorted = false;
-        while (last - first > 16) {
-            if (depth == 0) {  // heapsort fallback: never reached by real scenes, kept serial
-                if (lane == 0) sort_heapsort(A, first, last);
-                __syncwarp();
-                heapsorted = true;
-                break;
-            }
-            --depth;
-            const int mid = first + (last - first) / 2;
-            if (lane == 0) {  // __move_median_to_first(first, first+1, mid, last-1)
-                const int a = first + 1, b = mid, c = last - 1;
-                if (A.comp(a, b)) {
-                    if (A.comp(b, c)) A.swap(first, b);
-                    else if (A.comp(a, c)) A.swap(first, c);
-                    else A.swap(first, a);
-                } else if (A.comp(a, c)) A.swap(first, a);
-                else if (A.comp(b, c)) A.swap(first, c);
-                else A.swap(first, b);
-            }
-            __syncwarp();
-            int plo = first + 1, phi = last;
-            const float pivot = A.s[first];
-            warp_partition_wide(A, plo, phi, pivot);
-            const int cut = warp_partition(A, plo, phi, pivot, n);
-            stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
-            last = cut;
-        }
-        if (!heapsorted && last - first > 1) {  // a range the quicksort leaves to the final insertion sort
-            if (lane == 0) blocks[nblk] = ((unsigned) first << 16) | (unsigned) last;
-            nblk++;
-        }
+    for (int i = threadIdx.x; i < W.cap; i += blockDim.x) W.range[i] = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W.blocks[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int lg = 0;
+        for (int v = n; v > 1; v >>= 1) lg++;
+        W.depth[0] = (unsigned) (2 * lg);
+        W.range[0] = (unsigned) n;  // (0 << 16) | n
+        W.ctl[0] = 0; W.ctl[1] = 1; W.ctl[2] = 1; W.ctl[3] = 0;
     }
-    __syncwarp();
-    // __final_insertion_sort (__insertion_sort on the first 16, then __unguarded_insertion_sort): every
-    // element moves left past the elements it is greater than.  After the partitioning above the array is
-    // a sequence of ranges of <= 16 elements (or heap-sorted ones) with  left range >= pivot >= right range,
-    // so no element ever crosses into the range on its left (`val > y` is false for every y there) and the
-    // ranges can be insertion-sorted independently: one lane per range, same comparisons and moves per
-    // element as the sequential pass, hence the same permutation.
-    for (int b = lane; b < nblk; b += 32) {
-        const int first = (int) (blocks[b] >> 16), last = (int) (blocks[b] & 0xffffu);
-        for (int i = first + 1; i < last; ++i) {
-            const Cand val = A.get(i);
-            int j = i;
-            while (j > first && val.s > A.s[j - 1]) { A.set(j, A.get(j - 1)); --j; }
-            if (j != i) A.set(j, val);
+    __syncthreads();
+    for (;;) {
+        unsigned rng = 0u, dep = 0u;
+        if (lane == 0) {
+            const int t = atomicAdd(&W.ctl[0], 1);
+            if (t < W.cap) {
+                volatile unsigned* q = W.range;
+                for (;;) {
+                    rng = q[t];
+                    if (rng) break;
+                    if (*reinterpret_cast<volatile int*>(&W.ctl[2]) == 0) { rng = q[t]; break; }  // nothing will ever be pushed again
+                    __nanosleep(100);  // idle warps must not take shared-memory and issue slots from the working ones
+                }
+                if (rng) { __threadfence_block(); dep = reinterpret_cast<volatile unsigned*>(W.depth)[t]; }
+            }
         }
+        rng = __shfl_sync(0xffffffffu, rng, 0);
+        dep = __shfl_sync(0xffffffffu, dep, 0);
+        if (!rng) break;
+        __threadfence_block();
+        replay_range(A, n, (int) (rng >> 16), (int) (rng & 0xffffu), (int) dep, W);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicSub(&W.ctl[2], 1);
     }
-    __syncwarp();
+    __syncthreads();
+    // __final_insertion_sort (__insertion_sort on the first 16, then __unguarded_insertion_sort): every element moves left
+    // past the elements it is greater than (strict comparison: equal elements keep their order).  After the partitioning
+    // above the array is a sequence of ranges of <= 16 elements (or heap-sorted ones) with  left range >= pivot >= right
+    // range, so no element ever crosses into the range on its left and the pass is a STABLE sort of every range by
+    // itself: one thread per ELEMENT counts the elements of its range that end up before it (greater score, or equal
+    // score and earlier position) and, after a barrier, writes itself there -- the same permutation without the
+    // dependent load-store chain of a sequential insertion sort.
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        Cand val;
+        int dst = -1;
+        if (i < n && W.blocks[i]) {
+            const int first = (int) (W.blocks[i] >> 16), last = (int) (W.blocks[i] & 0xffffu);
+            val = A.get(i);
+            dst = first;
+            for (int j = first; j < last; j++) {
+                const float sj = A.s[j];
+                dst += (sj > val.s) || (sj == val.s && j < i);
+            }
+        }
+        __syncthreads();
+        if (dst >= 0) A.set(dst, val);
+        __syncthreads();
+    }
 }
+__host__ __device__ inline int replay_queue_cap(int n, int nthreads) { return n / 16 + 2 + nthreads / 32; }
 
 #ifdef EKP_CONN_PROFILE  // tools/ only: per-phase time of the slowest block and summed over blocks (ns)
 __device__ unsigned long long g_conn_prof[16];
@@ -368,57 +486,79 @@ __device__ __forceinline__ int ordered_slot(bool flag, int* sWarpCnt, int& base)
     return pos;
 }
 
-template <bool kVec2, int kT>
-__global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restrict__ line,
-                                                                   const int* __restrict__ part_off, int max_peaks,
-                                                                   const PafSource paf, int h1, Conn* __restrict__ conns,
-                                                                   int* __restrict__ n_conns,
-                                                                   unsigned* __restrict__ overflow) {
-    __shared__ ekp_peak sA[EKP_MAX_PART], sB[EKP_MAX_PART];
-    __shared__ float sScore[EKP_MAX_CAND];
-    __shared__ unsigned sTag[EKP_MAX_CAND];
-    __shared__ float sScore2[EKP_MAX_CAND];
-    __shared__ unsigned sTag2[EKP_MAX_CAND];   // pass-1 survivors while scoring, then the ranked tags
-    __shared__ int sTies;
-    __shared__ int sWarpCnt[kT / 32];
-    __shared__ unsigned sUsedA[EKP_MAX_PART / 32], sUsedB[EKP_MAX_PART / 32];
-    static_assert(kSurvWindow <= EKP_MAX_CAND, "the survivor list lives in sTag2");
-    const int limb = blockIdx.x, img = blockIdx.y;
-    const int pa = kPairs[limb][0], pb = kPairs[limb][1];
-    const int ch1 = kPairsNet[limb][0], ch2 = kPairsNet[limb][1];
-    const int* po = part_off + (size_t) img * 20;
-    const int offA = po[pa], offB = po[pb];
-    const int nA = min(po[pa + 1] - offA, EKP_MAX_PART), nB = min(po[pb + 1] - offB, EKP_MAX_PART);
-    int* out_n = n_conns + (size_t) img * EKP_NUM_LIMB + limb;
-    if (nA == 0 || nB == 0) {  // pafprocess.cpp:52-54
-        if (threadIdx.x == 0) *out_n = 0;
-        return;
-    }
-#ifdef EKP_CONN_PROFILE
-    unsigned long long prof_t = prof_now();
-#endif
-    const ekp_peak* L = line + (size_t) img * max_peaks;
-    for (int i = threadIdx.x; i < nA; i += kT) sA[i] = L[offA + i];
-    for (int i = threadIdx.x; i < nB; i += kT) sB[i] = L[offB + i];
-    if (threadIdx.x < EKP_MAX_PART / 32) sUsedA[threadIdx.x] = sUsedB[threadIdx.x] = 0u;
-    __syncthreads();
-
-    // ---- stage 4: score all nA x nB pairs; candidates end up in pair order (a outer, b inner) --------
-    PROF_MARK(0);  // peaks staged
+// ---- few pairs (every scene but a crowd): ten lanes per pair, one sample each -----------------------------------------
+// A thread that owns a whole pair has its 10 x (2..8) gathers serialised by its registers (several round trips to L2);
+// with a handful of pairs per block most threads would idle meanwhile.  Here a warp takes three pairs, lane 10 g + i
+// evaluates sample i of pair g with the same float operations as score_pair, and the group's first lane adds the ten
+// values in sample order (warp shuffles; pafprocess.cpp:78 is a sequential float sum) and applies both criteria: one
+// round trip to memory per three pairs per warp.  Candidates are compacted in pair order as everywhere else.
+template <int kSrc, int kT>
+__device__ __forceinline__ int score_pairs_by_sample(const PafSource& paf, const ekp_peak* __restrict__ sA, const ekp_peak* __restrict__ sB,
+                                                     int nA, int nB, int img, int ch1, int ch2, int h1, long long packed_base, int max_cand,
+                                                     float* __restrict__ sScore, unsigned* __restrict__ sTag, int* sWarpCnt) {
+    const unsigned FULL = 0xffffffffu;
     const int npairs = nA * nB;
-    long long packed_base = 0;  // PAF_PACKED (one image): where this limb's samples start in the pre-gathered list
-    if (paf.mode == PAF_PACKED) {
-        packed_base = paf.pair_base[limb];
-        if (npairs != paf.pair_base[limb + 1] - paf.pair_base[limb]) {  // the list was laid out for other counts: refuse
-            if (threadIdx.x == 0) { *out_n = 0; atomicOr(overflow + img, EKP_OVF_BADPEAK); }
-            return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / 10, i = lane - 10 * g;  // lanes 30, 31: g == 3, idle
+    constexpr int kPairsPerIter = 3 * (kT / 32);
+    int total = 0;
+    for (int base = 0; base < npairs; base += kPairsPerIter) {
+        const int pidx = base + 3 * warp + g;
+        const bool live = g < 3 && pidx < npairs;
+        float s = 0.f, vnorm = 0.f;
+        int ia = 0, ib = 0;
+        bool degenerate = true;
+        if (live) {
+            ia = pidx / nB;
+            ib = pidx - ia * nB;
+            const ekp_peak a = sA[ia], b = sB[ib];
+            const int dxi = b.x - a.x, dyi = b.y - a.y;
+            float vx = (float) dxi, vy = (float) dyi;
+            vnorm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+            degenerate = (double) vnorm < 1e-12;   // pafprocess.cpp:66
+            if (!degenerate) {
+                vx = __fdiv_rn(vx, vnorm);
+                vy = __fdiv_rn(vy, vnorm);
+                const float step_x = __fdiv_rn((float) dxi, 10.0f), step_y = __fdiv_rn((float) dyi, 10.0f);
+                const int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);  // roundpaf
+                const int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
+                const Sample2 sv = paf_sample<kSrc>(paf, nullptr, img, ly, lx, ch1, ch2, (packed_base + pidx) * 10 + i);
+                s = __fadd_rn(__fmul_rn(vx, sv.x), __fmul_rn(vy, sv.y));
+            }
         }
+        const unsigned above = __ballot_sync(FULL, live && !degenerate && s > 0.05f);
+        float scores = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 10; j++) scores = __fadd_rn(scores, __shfl_sync(FULL, s, min(10 * g, 20) + j));  // sample order 0..9
+        bool pass = false;
+        float crit = 0.f;
+        if (live && i == 0 && !degenerate) {
+            const int criterion1 = __popc(above & (0x3ffu << (10 * g)));
+            const double penalty = __dsub_rn(__ddiv_rn(__dmul_rn(0.5, (double) h1), (double) vnorm), 1.0);
+            const double mn = penalty < 0.0 ? penalty : 0.0;  // std::min(0.0, penalty)
+            crit = (float) __dadd_rn((double) __fdiv_rn(scores, 10.0f), mn);
+            pass = criterion1 > 6 && crit > 0.0f;
+        }
+        const int pos = ordered_slot<kT>(pass, sWarpCnt, total);  // group leaders are in pair order
+        if (pass && pos < max_cand) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
     }
+    return total;
+}
+
+// ---- stage 4 for one (limb, image): score all nA x nB pairs; candidates end up in pair order (a outer, b inner) in
+// sScore / sTag.  Returns the number of candidates (identical in every thread; may exceed max_cand: overflow).
+template <int kSrc, int kT>
+__device__ __forceinline__ int score_all_pairs(const PafSource& paf, const float2* __restrict__ sP, const ekp_peak* __restrict__ sA,
+                                               const ekp_peak* __restrict__ sB, int nA, int nB, int img, int ch1, int ch2, int h1,
+                                               long long packed_base, int max_cand, float* __restrict__ sScore,
+                                               unsigned* __restrict__ sTag, unsigned* __restrict__ sTag2, int* sWarpCnt) {
+    const int npairs = nA * nB;
     int total = 0;  // candidates so far, identical in every thread
     // Few pairs (every scene but a crowd): one pass, one round trip to memory.  Otherwise pass 1 thins them out.
     const bool two_pass = npairs > 2 * kT;
-    for (int win = 0; win < npairs; win += kSurvWindow) {
-        const int win_end = min(win + kSurvWindow, npairs);
+    const int surv_window = max_cand;  // pairs per pass-1 window: the survivor list lives in sTag2
+    for (int win = 0; win < npairs; win += surv_window) {
+        const int win_end = min(win + surv_window, npairs);
         int nsurv = 0;  // pass 1: pairs of this window that can still pass, in pair order
         if (!two_pass) {
             nsurv = win_end - win;
@@ -429,13 +569,12 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
             bool keep = false;
             if (pidx < win_end) {
                 const int ia = pidx / nB;
-                keep = pair_may_pass<kVec2>(sA[ia], sB[pidx - ia * nB], paf, img, ch1, ch2, (packed_base + pidx) * 10);
+                keep = pair_may_pass<kSrc>(sA[ia], sB[pidx - ia * nB], paf, sP, img, ch1, ch2, (packed_base + pidx) * 10);
             }
             const int pos = ordered_slot<kT>(keep, sWarpCnt, nsurv);
             if (keep) sTag2[pos] = (unsigned) pidx;
         }
         __syncthreads();
-        PROF_MARK(1);  // pass 1
         for (int base = 0; base < nsurv; base += kT) {  // pass 2: the full evaluation of the survivors
             const int k = base + threadIdx.x;
             bool pass = false;
@@ -445,23 +584,91 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
                 const int pidx = (int) sTag2[k];
                 ia = pidx / nB;
                 ib = pidx - ia * nB;
-                pass = score_pair<kVec2>(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit, (packed_base + pidx) * 10);
+                pass = score_pair<kSrc>(sA[ia], sB[ib], paf, sP, img, ch1, ch2, h1, crit, (packed_base + pidx) * 10);
             }
             const int pos = ordered_slot<kT>(pass, sWarpCnt, total);
-            if (pass && pos < EKP_MAX_CAND) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
+            if (pass && pos < max_cand) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
         }
         __syncthreads();  // the survivor list is rewritten by the next window
-        PROF_MARK(2);  // pass 2
     }
 
+    return total;
+}
+
+// Dynamic shared memory of one block: [float2 planes h*w (SRC_SMEM_PLANES only)] [sA, sB: max_part peaks each]
+// [sScore, sTag, sScore2, sTag2: max_cand words each].  max_part / max_cand are capacities of the context
+// (ekp_create_ex), reported through EKP_OVF_PART / EKP_OVF_CANDIDATES when a scene exceeds them.
+size_t connect_smem_bytes(int max_part, int max_cand, int plane_elems) {
+    return sizeof(float2) * (size_t) plane_elems + 2 * sizeof(ekp_peak) * (size_t) max_part + 4 * sizeof(float) * (size_t) max_cand;
+}
+
+template <int kSrc, int kT>
+__global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) {
+    extern __shared__ __align__(16) unsigned char conn_smem[];
+    const PafSource& paf = P.paf;
+    const int max_part = P.max_part, max_cand = P.max_cand;
+    float2* sPlane = reinterpret_cast<float2*>(conn_smem);
+    ekp_peak* sA = reinterpret_cast<ekp_peak*>(sPlane + (kSrc == SRC_SMEM_PLANES ? paf.h * paf.w : 0));
+    ekp_peak* sB = sA + max_part;
+    float* sScore = reinterpret_cast<float*>(sB + max_part);
+    unsigned* sTag = reinterpret_cast<unsigned*>(sScore + max_cand);
+    float* sScore2 = reinterpret_cast<float*>(sTag + max_cand);
+    unsigned* sTag2 = reinterpret_cast<unsigned*>(sScore2 + max_cand);   // pass-1 survivors while scoring, then the ranked tags
+    __shared__ int sTies;
+    __shared__ int sWarpCnt[kT / 32];
+    __shared__ int sReplayCtl[4];
+    __shared__ unsigned sUsedA[kMaxPartLimit / 32], sUsedB[kMaxPartLimit / 32];
+    const int limb = blockIdx.x, img = blockIdx.y;
+    const int pa = kPairs[limb][0], pb = kPairs[limb][1];
+    const int ch1 = kPairsNet[limb][0], ch2 = kPairsNet[limb][1];
+    const int* po = P.part_off + (size_t) img * 20;
+    const int offA = po[pa], offB = po[pb];
+    const int nA = min(po[pa + 1] - offA, max_part), nB = min(po[pb + 1] - offB, max_part);
+    int* out_n = P.n_conns + (size_t) img * EKP_NUM_LIMB + limb;
+    if (nA == 0 || nB == 0) {  // pafprocess.cpp:52-54
+        if (threadIdx.x == 0) *out_n = 0;
+        return;
+    }
+#ifdef EKP_CONN_PROFILE
+    unsigned long long prof_t = prof_now();
+#endif
+    const ekp_peak* L = P.line + (size_t) img * P.max_peaks;
+    for (int i = threadIdx.x; i < nA; i += kT) sA[i] = L[offA + i];
+    for (int i = threadIdx.x; i < nB; i += kT) sB[i] = L[offB + i];
+    if (threadIdx.x < kMaxPartLimit / 32) sUsedA[threadIdx.x] = sUsedB[threadIdx.x] = 0u;
+    // Staging the two planes pays when there are many pairs (a crowd); a handful of pairs is scored straight from L2,
+    // ten lanes per pair (block-uniform decisions; same values either way).
+    const bool staged = kSrc == SRC_SMEM_PLANES && nA * nB >= P.stage_min_pairs;
+    if (staged) stage_planes<kT>(sPlane, paf, img, ch1);
+    __syncthreads();
+
+    // ---- stage 4: score all nA x nB pairs; candidates end up in pair order (a outer, b inner) --------
+    PROF_MARK(0);  // peaks (and planes) staged
+    const int npairs = nA * nB;
+    long long packed_base = 0;  // PAF_PACKED (one image): where this limb's samples start in the pre-gathered list
+    if (paf.mode == PAF_PACKED) {
+        packed_base = paf.pair_base[limb];
+        if (npairs != paf.pair_base[limb + 1] - paf.pair_base[limb]) {  // the list was laid out for other counts: refuse
+            if (threadIdx.x == 0) { *out_n = 0; atomicOr(P.overflow + img, EKP_OVF_BADPEAK); }
+            return;
+        }
+    }
+    // The staged and the gathering form are separate instantiations of the scoring loops (a per-sample branch between
+    // them would keep the compiler from putting a pair's ten samples in flight together: 5x slower, measured).
+    constexpr int kGather = kSrc == SRC_SMEM_PLANES ? SRC_GLOBAL : kSrc;
+    int total;
+    if (staged) total = score_all_pairs<SRC_SMEM_PLANES, kT>(paf, sPlane, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sTag2, sWarpCnt);
+    else if (npairs <= P.by_sample_max_pairs) total = score_pairs_by_sample<kGather, kT>(paf, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sWarpCnt);
+    else total = score_all_pairs<kGather, kT>(paf, nullptr, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sTag2, sWarpCnt);
+    PROF_MARK(2);  // scoring (both passes)
     // ---- sort (pafprocess.cpp:97).  std::sort's result is only algorithm-dependent in how it
     // permutes EQUAL scores, and for n <= 16 it is a plain (stable) insertion sort.  So: rank every
     // candidate in parallel (stable order) and detect ties; only when n > 16 AND ties exist does
-    // one warp replay libstdc++'s introsort on the original sequence.
-    const int n = min(total, EKP_MAX_CAND);
+    // the block replay libstdc++'s introsort on the original sequence.
+    const int n = min(total, max_cand);
     if (threadIdx.x == 0) {
         sTies = 0;
-        if (total > EKP_MAX_CAND) atomicOr(overflow + img, EKP_OVF_CANDIDATES);
+        if (total > max_cand) atomicOr(P.overflow + img, EKP_OVF_CANDIDATES);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += kT) {
@@ -480,15 +687,20 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
     __syncthreads();
 
     PROF_MARK(3);  // rank sort
-    if (threadIdx.x >= 32) return;
-    const bool replay = n > 16 && sTies;  // uniform
-    if (replay) {                           // warp 0 replays libstdc++'s std::sort on the original sequence
+    const bool replay = n > 16 && sTies;  // uniform over the block
+    if (replay) {                          // all warps replay libstdc++'s std::sort on the original sequence
         CandArray A;
         A.s = sScore; A.t = sTag;
-        std_sort_desc(A, n, sTag2);  // the ranked copy is not needed when the replay decides the order
+        ReplayWork W;  // the ranked copy is not needed when the replay decides the order: its arrays hold the work lists
+        W.cap = replay_queue_cap(n, kT);
+        W.range = reinterpret_cast<unsigned*>(sScore2);
+        W.depth = W.range + W.cap;
+        W.blocks = sTag2;
+        W.ctl = sReplayCtl;
+        std_sort_desc_block(A, n, W);
     }
-    __syncwarp();
     PROF_MARK(4);  // std::sort replay
+    if (threadIdx.x >= 32) return;
     // ---- greedy assignment, pafprocess.cpp:98-124: walk the sorted candidates, accept one iff neither of its
     // peaks is used yet on this limb.  Warp 0 takes 32 candidates at a time: the lowest lane whose two peaks
     // are still free is the next accepted connection (same order as the sequential walk); its peaks
@@ -496,7 +708,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
     const float* srcS = replay ? sScore : sScore2;
     const unsigned* srcT = replay ? sTag : sTag2;
     const int lane = threadIdx.x;
-    Conn* out = conns + ((size_t) img * EKP_NUM_LIMB + limb) * EKP_MAX_PART;
+    Conn* out = P.conns + ((size_t) img * EKP_NUM_LIMB + limb) * max_part;
     int nc = 0;
     for (int c0 = 0; c0 < n; c0 += 32) {
         const int c = c0 + lane;
@@ -528,7 +740,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
     // the score sums the assembly needs per connection, here where 19 x n warps can fetch the peak scores in
     // parallel (one warp per image would pay the two dependent round trips alone)
     __syncwarp();
-    for (int k = lane; !paf.ids_are_rows && k < min(nc, EKP_MAX_PART); k += 32) {  // process_paf input: ids index the table
+    for (int k = lane; !paf.ids_are_rows && k < min(nc, max_part); k += 32) {  // process_paf input: ids index the table
         const float sc = out[k].score;
         const float p1 = L[out[k].cid1].score, p2 = L[out[k].cid2].score;
         out[k].s_ext = __fadd_rn(p2, sc);
@@ -548,12 +760,12 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ekp_peak* __restr
 __global__ void __launch_bounds__(kConnThreads) pair_sample_offsets_kernel(const ekp_peak* __restrict__ line,
                                                                            const int* __restrict__ part_off,
                                                                            const int* __restrict__ pair_base, int H, int W, int C,
-                                                                           unsigned* __restrict__ offs) {
+                                                                           int max_part, unsigned* __restrict__ offs) {
     const int limb = blockIdx.x;
     const int pa = kPairs[limb][0], pb = kPairs[limb][1];
     const int ch1 = kPairsNet[limb][0];
     const int offA = part_off[pa], offB = part_off[pb];
-    const int nA = min(part_off[pa + 1] - offA, EKP_MAX_PART), nB = min(part_off[pb + 1] - offB, EKP_MAX_PART);
+    const int nA = min(part_off[pa + 1] - offA, max_part), nB = min(part_off[pb + 1] - offB, max_part);
     const int npairs = nA * nB;
     if (npairs != pair_base[limb + 1] - pair_base[limb]) return;  // the host counted differently: it will not use the list
     unsigned* out = offs + (size_t) pair_base[limb] * 10;
@@ -573,40 +785,93 @@ __global__ void __launch_bounds__(kConnThreads) pair_sample_offsets_kernel(const
     }
 }
 cudaError_t launch_pair_sample_offsets(const ekp_peak* line, const int* part_off, const int* pair_base, int H, int W, int C,
-                                       unsigned* offs, cudaStream_t stream) {
-    pair_sample_offsets_kernel<<<EKP_NUM_LIMB, kConnThreads, 0, stream>>>(line, part_off, pair_base, H, W, C, offs);
+                                       int max_part, unsigned* offs, cudaStream_t stream) {
+    pair_sample_offsets_kernel<<<EKP_NUM_LIMB, kConnThreads, 0, stream>>>(line, part_off, pair_base, H, W, C, max_part, offs);
     return cudaGetLastError();
 }
 
-// Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one warp), so that the tie permutation -- including the heapsort fallback, which real scenes never
-// reach -- can be compared with the compiled reference's std::sort.
-__global__ void debug_std_sort_kernel(float* scores, unsigned* tags, int n, unsigned* scratch) {
-    CandArray A;  // one warp, as in paf_connect_kernel
+// Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one block, as in
+// paf_connect_kernel), so that the tie permutation -- including the heapsort fallback, which real scenes never
+// reach -- can be compared with the compiled reference's std::sort.  scratch: n + 2 * replay_queue_cap words.
+constexpr int kDebugSortThreads = 256;
+__global__ void __launch_bounds__(kDebugSortThreads) debug_std_sort_kernel(float* scores, unsigned* tags, int n, unsigned* scratch) {
+    __shared__ int ctl[4];
+    CandArray A;
     A.s = scores; A.t = tags;
-    std_sort_desc(A, n, scratch);
+    ReplayWork W;
+    W.cap = replay_queue_cap(n, kDebugSortThreads);
+    W.blocks = scratch;
+    W.range = scratch + n;
+    W.depth = W.range + W.cap;
+    W.ctl = ctl;
+    std_sort_desc_block(A, n, W);
 }
+size_t debug_std_sort_scratch_words(int n) { return (size_t) n + 2 * (size_t) replay_queue_cap(n, kDebugSortThreads); }
 cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned* scratch, cudaStream_t stream) {
-    debug_std_sort_kernel<<<1, 32, 0, stream>>>(scores, tags, n, scratch);
+    debug_std_sort_kernel<<<1, kDebugSortThreads, 0, stream>>>(scores, tags, n, scratch);
     return cudaGetLastError();
 }
 
-cudaError_t launch_paf_connect(const ekp_peak* line, const int* part_off, int max_peaks, const PafSource& paf, int h1,
-                               int n, Conn* conns, int* n_conns, unsigned* overflow, cudaStream_t stream) {
-    dim3 grid(EKP_NUM_LIMB, n);
-    // both PAF channels of a limb with one 8-byte load: channel-last tensor, even channel count, aligned base
-    const bool channel_last = paf.mode != PAF_PACKED && (paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC);
-    const bool vec2 = channel_last && paf.C % 2 == 0 && reinterpret_cast<uintptr_t>(paf.ptr) % 8 == 0;
-    // Blocks are latency-bound chains; a batch whose 19 x n blocks all fit on the GPU at once (crowded scenes come in
-    // small batches) gets twice the threads per block, bigger batches keep more blocks resident instead.
+// ---- launch ------------------------------------------------------------------------------------------------
+// Source: shared-memory planes when the stride-8 PAF is NCHW (the network's layout; coalesced staging) and the
+// planes fit; otherwise gathers from global memory, 8-byte ones when the tensor is channel-last, even and aligned.
+// Threads: blocks are latency-bound chains; a batch whose 19 x n blocks all fit on the GPU at once (crowded scenes
+// come in small batches) gets more threads per block, bigger batches keep more blocks resident instead; big planes
+// (one or two blocks per SM) get 512.
+constexpr size_t kSmemPerSm = 227 * 1024;
+static bool planes_fit(const PafSource& paf, int max_part, int max_cand) {
+    return (paf.mode == PAF_LO_NEAREST || paf.mode == PAF_LO_BILINEAR) && paf.layout == EKP_LAYOUT_NCHW &&
+           connect_smem_bytes(max_part, max_cand, paf.h * paf.w) <= 200 * 1024;
+}
+
+template <int kSrc, int kT>
+static cudaError_t launch_one(const ConnectParams& P, int n, size_t smem, cudaStream_t stream) {
+    paf_connect_kernel<kSrc, kT><<<dim3(EKP_NUM_LIMB, n), kT, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+template <int kSrc>
+static cudaError_t launch_src(const ConnectParams& P, int n, size_t smem, int threads, cudaStream_t stream) {
+    if (threads == 512) return launch_one<kSrc, 512>(P, n, smem, stream);
+    if (threads == 256) return launch_one<kSrc, 256>(P, n, smem, stream);
+    return launch_one<kSrc, 128>(P, n, smem, stream);
+}
+
+// per device, once per context: allow the largest dynamic shared memory this context can ask for
+cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w) {
+    size_t big = connect_smem_bytes(max_part, max_cand, max_h * max_w);
+    if (big > 200 * 1024) big = connect_smem_bytes(max_part, max_cand, 0);
+    if (big > kSmemPerSm) return cudaErrorInvalidValue;
+    cudaError_t e = cudaSuccess;
+#define EKP_RAISE(S, T) if (e == cudaSuccess) e = raise_dynamic_smem_limit(paf_connect_kernel<S, T>, big)
+    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256); EKP_RAISE(SRC_GLOBAL, 512);
+    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256); EKP_RAISE(SRC_GLOBAL_VEC2, 512);
+    EKP_RAISE(SRC_SMEM_PLANES, 128); EKP_RAISE(SRC_SMEM_PLANES, 256); EKP_RAISE(SRC_SMEM_PLANES, 512);
+#undef EKP_RAISE
+    return e;
+}
+
+cudaError_t launch_paf_connect(const ConnectParams& P_in, int n, cudaStream_t stream) {
+    ConnectParams P = P_in;
+    const PafSource& paf = P.paf;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool wide = EKP_NUM_LIMB * n <= 4 * sms;
-#define EKP_LAUNCH_CONNECT(V, T) paf_connect_kernel<V, T><<<grid, T, 0, stream>>>(line, part_off, max_peaks, paf, h1, conns, n_conns, overflow)
-    if (vec2) { if (wide) EKP_LAUNCH_CONNECT(true, 2 * kConnThreads); else EKP_LAUNCH_CONNECT(true, kConnThreads); }
-    else { if (wide) EKP_LAUNCH_CONNECT(false, 2 * kConnThreads); else EKP_LAUNCH_CONNECT(false, kConnThreads); }
-#undef EKP_LAUNCH_CONNECT
-    return cudaGetLastError();
+    const bool staged = planes_fit(paf, P.max_part, P.max_cand);
+    const size_t smem = connect_smem_bytes(P.max_part, P.max_cand, staged ? paf.h * paf.w : 0);
+    const int blocks = EKP_NUM_LIMB * n;
+    int threads = blocks <= 4 * sms ? 2 * kConnThreads : kConnThreads;
+    if (staged && smem > 64 * 1024 && blocks <= 4 * sms) threads = 512;
+    // per-block regimes (same results in all of them): up to six rounds of ten-lanes-per-pair scoring straight from L2,
+    // beyond that one thread per pair in two exact passes, on planes staged in shared memory where the launch has them
+    static const int env_by_sample = getenv("EKP_BY_SAMPLE_MAX_PAIRS") ? atoi(getenv("EKP_BY_SAMPLE_MAX_PAIRS")) : -1;
+    static const int env_stage_min = getenv("EKP_STAGE_MIN_PAIRS") ? atoi(getenv("EKP_STAGE_MIN_PAIRS")) : -1;
+    P.by_sample_max_pairs = env_by_sample >= 0 ? env_by_sample : 6 * 3 * (threads / 32);
+    P.stage_min_pairs = env_stage_min >= 0 ? env_stage_min : P.by_sample_max_pairs + 1;
+    if (staged) return launch_src<SRC_SMEM_PLANES>(P, n, smem, threads, stream);
+    // both PAF channels of a limb with one 8-byte load: channel-last tensor, even channel count, aligned base
+    const bool channel_last = paf.mode != PAF_PACKED && (paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC);
+    const bool vec2 = channel_last && paf.C % 2 == 0 && reinterpret_cast<uintptr_t>(paf.ptr) % 8 == 0;
+    return vec2 ? launch_src<SRC_GLOBAL_VEC2>(P, n, smem, threads, stream) : launch_src<SRC_GLOBAL>(P, n, smem, threads, stream);
 }
 
 }  // namespace ekp

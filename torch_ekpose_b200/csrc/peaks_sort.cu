@@ -44,7 +44,7 @@ __global__ void peaks_ingest_kernel(const float* __restrict__ peaks, const int* 
 // offsets.  Crowded images (hundreds of peaks) thus spread over several SMs instead of one.
 constexpr int kSortThreads = 256;
 __global__ void __launch_bounds__(kSortThreads) peaks_sort_kernel(const RawPeak* __restrict__ raw, const int* __restrict__ raw_count,
-                                                                  int raw_cap, int id_from_key, ekp_peak* __restrict__ line,
+                                                                  int raw_cap, int max_part, int id_from_key, ekp_peak* __restrict__ line,
                                                                   int* __restrict__ part_off /* [n][20] */,
                                                                   int* __restrict__ n_peaks, unsigned* __restrict__ overflow) {
     extern __shared__ unsigned long long sKey[];
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kSortThreads) peaks_sort_kernel(const RawPeak*
         int* po = part_off + (size_t) img * 20;
         for (int p = 0; p < EKP_NUM_PART; p++) {
             po[p] = off;
-            if (sCount[p] > EKP_MAX_PART) ovf |= EKP_OVF_PART;
+            if (sCount[p] > max_part) ovf |= EKP_OVF_PART;
             off += sCount[p];
         }
         po[EKP_NUM_PART] = off;   // == number of valid peaks (invalid ones sort behind)
@@ -105,11 +105,11 @@ cudaError_t configure_peaks_sort(int raw_cap) {
     return raise_dynamic_smem_limit(peaks_sort_kernel, sizeof(unsigned long long) * (size_t) raw_cap);
 }
 
-cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int id_from_key, int n, ekp_peak* line,
+cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int max_part, int id_from_key, int n, ekp_peak* line,
                               int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream) {
     const size_t smem = sizeof(unsigned long long) * (size_t) raw_cap;
     dim3 grid((raw_cap + kSortThreads - 1) / kSortThreads, n);
-    peaks_sort_kernel<<<grid, kSortThreads, smem, stream>>>(raw, raw_count, raw_cap, id_from_key, line, part_off, n_peaks, overflow);
+    peaks_sort_kernel<<<grid, kSortThreads, smem, stream>>>(raw, raw_count, raw_cap, max_part, id_from_key, line, part_off, n_peaks, overflow);
     return cudaGetLastError();
 }
 

@@ -52,12 +52,16 @@ class PostProcessor:
     """
 
     def __init__(self, device: int = 0, max_batch: int = 64, max_h: int = 46, max_w: int = 54, max_peaks: int = 1024,
-                 max_humans: int = 64):
+                 max_humans: int = 64, max_part: int = 0, max_cand: int = 0):
+        """max_part / max_cand: peaks of one part / passing candidates of one limb per image (0 = the library
+        defaults EKP_MAX_PART 256 / EKP_MAX_CAND 2048); a scene beyond any capacity raises EkpCapacityError."""
         self.device = int(device)
         self._ctx = C.c_void_p()
-        _lib.check(_lib.lib.ekp_create(C.byref(self._ctx), self.device, max_batch, max_h, max_w, max_peaks, max_humans))
+        _lib.check(_lib.lib.ekp_create_ex(C.byref(self._ctx), self.device, max_batch, max_h, max_w, max_peaks, max_humans,
+                                          max_part, max_cand))
         self.max_batch, self.max_h, self.max_w = max_batch, max_h, max_w
         self.max_peaks, self.max_humans = max_peaks, max_humans
+        self.max_part, self.max_cand = int(_lib.lib.ekp_max_part(self._ctx)), int(_lib.lib.ekp_max_cand(self._ctx))
         self._keep = None      # inputs of the in-flight run
         self._n = 0
         self._hw = (0, 0)
@@ -99,10 +103,12 @@ class PostProcessor:
                              f"{tuple(heat_shape)} / {tuple(paf_shape)} ({layout})")
         return int(n), int(h), int(w)
 
-    def run(self, heat, paf, *, layout: str = "nchw", frontend: str = "dense", thr: float = 0.15,
+    def run(self, heat, paf, *, layout: str = "nchw", frontend: str = "reference", thr: float = 0.15,
             materialize: bool = False, stream=None) -> None:
         """Submit one batch (n <= max_batch).  CUDA tensors take the device entry point; NumPy
-        arrays / CPU tensors take the host entry point (H2D copies on the same stream)."""
+        arrays / CPU tensors take the host entry point (H2D copies on the same stream).
+        frontend: 'reference' (default: the reference's own stride-8 NMS + bicubic refinement, i.e. the people
+        paf_to_pose_cpp returns), 'dense' (the north_star formulation) or 'reference_coarse'."""
         if frontend not in _FRONTENDS:
             raise ValueError("frontend must be 'dense', 'reference' or 'reference_coarse'")
         n, h, w = self._dims(heat.shape, paf.shape, layout)
@@ -242,6 +248,10 @@ class PostProcessor:
     def kernel_launches(self) -> int:
         return int(_lib.lib.ekp_kernel_launches(self._ctx))
 
+    def graph_launches(self) -> int:
+        """Batches replayed as a CUDA graph (same pointers, shape and flags as an earlier batch)."""
+        return int(_lib.lib.ekp_graph_launches(self._ctx))
+
     def dense_smooth(self, heat, layout: str = "nchw"):
         """Test hook: the dense front-end's smoothed map, CUDA tensor [n, 8h, 8w, 18]."""
         if layout == "nchw":
@@ -255,42 +265,127 @@ class PostProcessor:
         return out
 
 
+class PinnedBatch:
+    """One pinned host block holding a batch's heat tensor directly followed by its PAF tensor (NCHW or NHWC):
+    ``PostProcessor.run(b.heat, b.paf, ...)`` then moves both with a single host-to-device copy.
+    ``heat`` / ``paf`` are NumPy views to fill in place."""
+
+    def __init__(self, n: int, h: int, w: int, layout: str = "nchw", write_combined: bool = False):
+        self._ptr = C.c_void_p()
+        nh, npf = n * h * w * _lib.HEAT_CH, n * h * w * _lib.PAF_CH
+        _lib.check(_lib.lib.ekp_host_alloc(C.byref(self._ptr), 4 * (nh + npf), int(bool(write_combined))))
+        buf = (C.c_float * (nh + npf)).from_address(self._ptr.value)
+        flat = np.frombuffer(buf, dtype=np.float32)
+        shp = (lambda c: (n, c, h, w)) if layout == "nchw" else (lambda c: (n, h, w, c))
+        self.heat = flat[:nh].reshape(shp(_lib.HEAT_CH))
+        self.paf = flat[nh:].reshape(shp(_lib.PAF_CH))
+        self.nbytes = 4 * (nh + npf)
+
+    def close(self):
+        if getattr(self, "_ptr", None) and self._ptr.value:
+            self.heat = self.paf = None
+            _lib.lib.ekp_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- module-level convenience API ---------------------------------------------------------------
 _cache: dict = {}
 
 
-def _processor(device: int, n: int, h: int, w: int, max_peaks: int, max_humans: int) -> PostProcessor:
+def _default_device() -> int:
+    """EKP_DEVICE (the same variable the C operator surface reads) or 0."""
+    import os
+    return int(os.environ.get("EKP_DEVICE", "0"))
+
+
+def _processor(device: int, n: int, h: int, w: int, max_peaks: int, max_humans: int, max_part: int = 0, max_cand: int = 0) -> PostProcessor:
+    """The cached context of ``device``, re-created (new one first, then the old one closed) when a dimension or a
+    capacity is too small; a failed creation leaves no stale entry behind."""
     key = (device,)
     pp = _cache.get(key)
-    if pp is None or pp.max_batch < n or pp.max_h < h or pp.max_w < w or pp.max_peaks < max_peaks or pp.max_humans < max_humans:
+    want_part, want_cand = max_part or _lib.MAX_PART, max_cand or _lib.MAX_CAND
+    if pp is not None and pp.max_batch >= n and pp.max_h >= h and pp.max_w >= w and pp.max_peaks >= max_peaks and \
+            pp.max_humans >= max_humans and pp.max_part >= want_part and pp.max_cand >= want_cand:
+        return pp
+    if pp is not None:
+        max_peaks, max_humans = max(max_peaks, pp.max_peaks), max(max_humans, pp.max_humans)
+        want_part, want_cand = max(want_part, pp.max_part), max(want_cand, pp.max_cand)
+        n, h, w = max(n, pp.max_batch), max(h, pp.max_h), max(w, pp.max_w)
+    try:
+        new = PostProcessor(device, n, h, w, max_peaks, max_humans, want_part, want_cand)
+    except Exception:
+        _cache.pop(key, None)
         if pp is not None:
             pp.close()
-            max_peaks, max_humans = max(max_peaks, pp.max_peaks), max(max_humans, pp.max_humans)
-            n, h, w = max(n, pp.max_batch), max(h, pp.max_h), max(w, pp.max_w)
-        pp = _cache[key] = PostProcessor(device, n, h, w, max_peaks, max_humans)
-    return pp
+        raise
+    if pp is not None:
+        pp.close()
+    _cache[key] = new
+    return new
 
 
-def postprocess_batch(heat, paf, *, layout: str = "nchw", frontend: str = "dense", thr: float = 0.15,
-                      materialize: bool = False, max_peaks: int = 2048, max_humans: int = 128,
-                      device: Optional[int] = None) -> List[List[Human]]:
-    """heat [n,19,h,w] / paf [n,38,h,w] (or NHWC) -> per-image list[Human].  CUDA tensors stay on
-    the device; host arrays are copied in.  On a capacity overflow the buffers are grown once."""
+def _grow(pp: PostProcessor, bits: int):
+    """Capacities for a retry after the overflow ``bits``: only what overflowed grows (x4), clamped to the library's
+    limits; None when nothing that overflowed can still grow."""
+    caps = dict(max_peaks=pp.max_peaks, max_humans=pp.max_humans, max_part=pp.max_part, max_cand=pp.max_cand)
+    lim = dict(max_peaks=_lib.LIMIT_PEAKS, max_humans=_lib.LIMIT_HUMANS, max_part=_lib.LIMIT_PART, max_cand=_lib.LIMIT_CAND)
+    grew = False
+    for bit, name in ((_lib.OVF_PEAKS, "max_peaks"), (_lib.OVF_HUMANS, "max_humans"), (_lib.OVF_PART, "max_part"),
+                      (_lib.OVF_CANDIDATES, "max_cand")):
+        if bits & bit:
+            if caps[name] >= lim[name]:
+                return None
+            caps[name] = min(caps[name] * 4, lim[name])
+            grew = True
+    return caps if grew else None
+
+
+def _run_growing(device, heat, paf, n, h, w, caps, fatal_bits, **run_kw) -> PostProcessor:
+    """Run one batch on the cached context of ``device``, growing the capacities named by the overflow bits in
+    ``fatal_bits`` until the batch fits (other bits are the caller's business)."""
+    while True:
+        pp = _processor(device, n, h, w, **caps)
+        pp.run(heat, paf, **run_kw)
+        res = pp.results(raise_on_overflow=False)
+        bits = int(np.bitwise_or.reduce(res["overflow"])) if len(res["overflow"]) else 0
+        if bits & _lib.OVF_BADPEAK:
+            raise _lib.EkpError(_lib.ERR_ARG, "non-finite values in the input maps")
+        if not bits & fatal_bits:
+            return pp
+        caps = _grow(pp, bits & fatal_bits)
+        if caps is None:
+            raise _lib.EkpCapacityError(_lib.ERR_CAPACITY, f"the batch exceeds the library's limits (overflow bits 0x{bits:x}: "
+                                        f"peaks {_lib.LIMIT_PEAKS}, humans {_lib.LIMIT_HUMANS}, peaks per part {_lib.LIMIT_PART}, "
+                                        f"candidates per limb {_lib.LIMIT_CAND})")
+
+
+_ALL_OVF = _lib.OVF_PEAKS | _lib.OVF_PART | _lib.OVF_CANDIDATES | _lib.OVF_HUMANS
+
+
+def postprocess_batch(heat, paf, *, layout: str = "nchw", frontend: str = "reference", thr: float = 0.15,
+                      materialize: bool = False, max_peaks: int = 2048, max_humans: int = 128, max_part: int = 0,
+                      max_cand: int = 0, device: Optional[int] = None) -> List[List[Human]]:
+    """heat [n,19,h,w] / paf [n,38,h,w] (or NHWC) -> per-image list[Human].  CUDA tensors stay on their
+    device; host arrays are copied to ``device`` (default EKP_DEVICE or 0).  The default front-end is the
+    reference's own, so the people equal ``paf_to_pose_cpp``'s; ``frontend='dense'`` selects the north_star
+    formulation.  A capacity overflow grows the capacity that overflowed (within the library's limits) and retries."""
     if device is None:
-        device = heat.device.index if (_is_tensor(heat) and heat.is_cuda) else 0
+        device = heat.device.index if (_is_tensor(heat) and heat.is_cuda) else _default_device()
     shp = heat.shape
     n, h, w = (shp[0], shp[2], shp[3]) if layout == "nchw" else (shp[0], shp[1], shp[2])
-    for _ in range(3):
-        pp = _processor(device, int(n), int(h), int(w), max_peaks, max_humans)
-        pp.run(heat, paf, layout=layout, frontend=frontend, thr=thr, materialize=materialize)
-        try:
-            return pp.humans()
-        except _lib.EkpCapacityError:
-            max_peaks, max_humans = pp.max_peaks * 4, min(pp.max_humans * 4, 2048)
-    raise _lib.EkpCapacityError(_lib.ERR_CAPACITY, "result does not fit even after growing the buffers")
+    caps = dict(max_peaks=max_peaks, max_humans=max_humans, max_part=max_part, max_cand=max_cand)
+    pp = _run_growing(device, heat, paf, int(n), int(h), int(w), caps, _ALL_OVF, layout=layout, frontend=frontend, thr=thr,
+                      materialize=materialize)
+    return pp.humans()
 
 
-def paf_to_pose_cpp(heatmaps, pafs, config=None, *, frontend: str = "reference") -> List[Human]:
+def paf_to_pose_cpp(heatmaps, pafs, config=None, *, frontend: str = "reference", device: Optional[int] = None) -> List[Human]:
     """Drop-in for paf_to_pose.py:346-380: one image, numpy HWC ``heatmaps[h,w,19]``,
     ``pafs[h,w,38]`` (the arrays estimator.get_outputs returns) -> ``list[Human]``.
 
@@ -312,7 +407,7 @@ def paf_to_pose_cpp(heatmaps, pafs, config=None, *, frontend: str = "reference")
         heat4, paf4, layout = hv[None], pv[None], "nchw"   # a view of the network's CHW output: no copy
     else:
         heat4, paf4 = heatmaps[None], pafs[None]
-    return postprocess_batch(heat4, paf4, layout=layout, frontend=frontend, thr=config.TEST.THRESH_HEATMAP)[0]
+    return postprocess_batch(heat4, paf4, layout=layout, frontend=frontend, thr=config.TEST.THRESH_HEATMAP, device=device)[0]
 
 
 def compute_resized_coords(coords, resizeFactor):
@@ -320,24 +415,19 @@ def compute_resized_coords(coords, resizeFactor):
     return (np.array(coords, dtype=float) + 0.5) * resizeFactor - 0.5
 
 
-def _coarse_peaks(heat_hwc: np.ndarray, thr: float):
-    """Stride-8 maxima of every part map on the GPU: (line, part_off) of the part-sorted peak table, rows at
-    (8x + 3, 8y + 3) in (part, y, x) order."""
+def _peak_table(heat_hwc: np.ndarray, thr: float, frontend: str, device: Optional[int]):
+    """Stages 1-3 of one map on the GPU: (line, part_off) of the part-sorted peak table in (part, y, x) order.  Only the
+    peak table matters here: more peaks of one part than max_part (or whatever stages 4-5 ran into on an arbitrary
+    map) does not cut it, more than max_peaks does -- that capacity grows."""
     h, w, _ = heat_hwc.shape
-    pp = _processor(0, 1, h, w, 2048, 128)
-    while True:
-        pp.run(heat_hwc[None], np.zeros((1, h, w, _lib.PAF_CH), np.float32), layout="nhwc", frontend="reference_coarse", thr=thr)
-        # only the peak table matters here: more than EKP_MAX_PART peaks of one part (or whatever stages 4-5 ran
-        # into on an arbitrary map) does not cut it, more than max_peaks does
-        res = pp.results(with_peaks=True, raise_on_overflow=False)
-        if not int(res["overflow"][0]) & _lib.OVF_PEAKS:
-            return res["peaks"][0], res["part_off"][0]
-        if pp.max_peaks >= 16384:
-            raise _lib.EkpCapacityError(_lib.ERR_CAPACITY, "more than 16384 peaks in one image")
-        pp = _processor(0, 1, h, w, min(pp.max_peaks * 4, 16384), 128)
+    device = _default_device() if device is None else device
+    pp = _run_growing(device, heat_hwc[None], np.zeros((1, h, w, _lib.PAF_CH), np.float32), 1, h, w,
+                      dict(max_peaks=2048, max_humans=128), _lib.OVF_PEAKS, layout="nhwc", frontend=frontend, thr=thr)
+    res = pp.results(with_peaks=True, raise_on_overflow=False)
+    return res["peaks"][0], res["part_off"][0]
 
 
-def find_peaks(param, img):
+def find_peaks(param, img, device: Optional[int] = None):
     """Drop-in for paf_to_pose.py:26-36: the local maxima (4-neighbour cross, in-bounds neighbours only) of a 2-D
     map that exceed ``param``, as an int array of [x, y] rows in row-major order.  Runs on the GPU (the map
     travels as part 0 of an otherwise empty heat tensor)."""
@@ -349,12 +439,12 @@ def find_peaks(param, img):
         raise ValueError("the CUDA path needs maps of at least 5 x 5")
     heat = np.full((h, w, _lib.HEAT_CH), -np.inf, np.float32)
     heat[:, :, 0] = img
-    line, po = _coarse_peaks(heat, float(param))
+    line, po = _peak_table(heat, float(param), "reference_coarse", device)
     rows = line[po[0]:po[1]]
     return np.stack([(rows["x"] - 3) // 8, (rows["y"] - 3) // 8], axis=1).astype(np.int64).reshape(-1, 2)
 
 
-def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False, config=None):
+def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False, config=None, device: Optional[int] = None):
     """Drop-in for paf_to_pose.py:60-133: list of 18 float64 arrays ``[n_k, 4]`` = (x, y, score, id).
     bool_refine_center=False returns the stride-8 maxima at compute_resized_coords(peak, 8) with the heat value
     as score (:119-122)."""
@@ -365,7 +455,7 @@ def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=F
     heatmaps = np.ascontiguousarray(heatmaps, np.float32)
     h, w, _ = heatmaps.shape
     if not bool_refine_center:
-        line, po = _coarse_peaks(heatmaps, config.TEST.THRESH_HEATMAP)
+        line, po = _peak_table(heatmaps, config.TEST.THRESH_HEATMAP, "reference_coarse", device)
         out = []
         for k in range(config.MODEL.NUM_KEYPOINTS):
             rows = line[po[k]:po[k + 1]]
@@ -375,11 +465,7 @@ def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=F
             arr[:, 2], arr[:, 3] = rows["score"], rows["id"]
             out.append(arr)
         return out
-    pp = _processor(0, 1, h, w, 2048, 128)
-    pp.run(heatmaps[None], np.zeros((1, h, w, _lib.PAF_CH), np.float32), layout="nhwc", frontend="reference",
-           thr=config.TEST.THRESH_HEATMAP)
-    res = pp.results(with_peaks=True)
-    line, po = res["peaks"][0], res["part_off"][0]
+    line, po = _peak_table(heatmaps, config.TEST.THRESH_HEATMAP, "reference", device)
     out = []
     for k in range(config.MODEL.NUM_KEYPOINTS):
         rows = line[po[k]:po[k + 1]]
