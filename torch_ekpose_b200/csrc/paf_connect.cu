@@ -331,6 +331,7 @@ struct ReplayWork {
     unsigned* depth;   // queue: depth limit left for that range
     int cap;           // queue entries (>= pushes + number of warps)
     unsigned* blocks;  // [n] per element: the range (packed like `range`) the final insertion sort handles it in, 0 = none
+    unsigned* tmp;     // [n] scratch of the final permutation (may alias range / depth: the queue is idle by then)
     int* ctl;          // [4]: head (next ticket), tail (next free entry), pending (ranges pushed and not finished)
 };
 
@@ -429,25 +430,32 @@ __device__ void std_sort_desc_block(const CandArray& A, int n, const ReplayWork&
     // above the array is a sequence of ranges of <= 16 elements (or heap-sorted ones) with  left range >= pivot >= right
     // range, so no element ever crosses into the range on its left and the pass is a STABLE sort of every range by
     // itself: one thread per ELEMENT counts the elements of its range that end up before it (greater score, or equal
-    // score and earlier position) and, after a barrier, writes itself there -- the same permutation without the
-    // dependent load-store chain of a sequential insertion sort.
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        Cand val;
-        int dst = -1;
-        if (i < n && W.blocks[i]) {
+    // score and earlier position); then all elements move at once -- the same permutation without the dependent
+    // load-store chain of a sequential insertion sort.
+    // pass 1: every element's destination (its own word of `blocks` is overwritten with it; nobody else reads that word)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int dst = i;
+        if (W.blocks[i]) {
             const int first = (int) (W.blocks[i] >> 16), last = (int) (W.blocks[i] & 0xffffu);
-            val = A.get(i);
+            const float v = A.s[i];
             dst = first;
             for (int j = first; j < last; j++) {
                 const float sj = A.s[j];
-                dst += (sj > val.s) || (sj == val.s && j < i);
+                dst += (sj > v) || (sj == v && j < i);
             }
         }
-        __syncthreads();
-        if (dst >= 0) A.set(dst, val);
-        __syncthreads();
+        W.blocks[i] = (unsigned) dst;
     }
+    __syncthreads();
+    // pass 2: permute through `tmp` (the work queue's memory, idle by now), scores then tags
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W.tmp[W.blocks[i]] = __float_as_uint(A.s[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) A.s[i] = __uint_as_float(W.tmp[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W.tmp[W.blocks[i]] = A.t[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) A.t[i] = W.tmp[i];
+    __syncthreads();
 }
 __host__ __device__ inline int replay_queue_cap(int n, int nthreads) { return n / 16 + 2 + nthreads / 32; }
 
@@ -696,6 +704,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) 
         W.range = reinterpret_cast<unsigned*>(sScore2);
         W.depth = W.range + W.cap;
         W.blocks = sTag2;
+        W.tmp = reinterpret_cast<unsigned*>(sScore2);
         W.ctl = sReplayCtl;
         std_sort_desc_block(A, n, W);
     }
@@ -707,6 +716,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) 
     // knock out the other lanes' candidates, and the used sets carry over to the next 32.
     const float* srcS = replay ? sScore : sScore2;
     const unsigned* srcT = replay ? sTag : sTag2;
+    unsigned* sAcc = replay ? sTag2 : sTag;   // accepted candidates, in acceptance order (the array the sort left free)
     const int lane = threadIdx.x;
     Conn* out = P.conns + ((size_t) img * EKP_NUM_LIMB + limb) * max_part;
     int nc = 0;
@@ -721,13 +731,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) 
             const int leader = __ffs(m) - 1;
             const int l1 = __shfl_sync(0xffffffffu, i1, leader), l2 = __shfl_sync(0xffffffffu, i2, leader);
             if (lane == leader) {
-                Conn cn;
-                cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c];
-                const float ps1 = sA[i1].score, ps2 = sB[i2].score;  // == peak_infos_line[cid].score when ids are rows
-                cn.s_ext = __fadd_rn(ps2, cn.score);
-                cn.s_new = __fadd_rn(__fadd_rn(ps1, ps2), cn.score);
-                cn.pad0 = cn.pad1 = cn.pad2 = 0;
-                out[nc] = cn;
+                sAcc[nc] = (unsigned) c;
                 sUsedA[i1 >> 5] |= 1u << (i1 & 31);
                 sUsedB[i2 >> 5] |= 1u << (i2 & 31);
             }
@@ -735,6 +739,19 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) 
             nc++;
         }
         __syncwarp();  // the used sets are read by every lane at the top of the next chunk
+    }
+    // the accepted connections, written by all lanes at once (pafprocess.cpp:117-123)
+    for (int k = lane; k < nc; k += 32) {
+        const int c = (int) sAcc[k];
+        const unsigned tag = srcT[c];
+        const int i1 = tag >> 16, i2 = tag & 0xffff;
+        Conn cn;
+        cn.cid1 = sA[i1].id; cn.cid2 = sB[i2].id; cn.score = srcS[c];
+        const float ps1 = sA[i1].score, ps2 = sB[i2].score;  // == peak_infos_line[cid].score when ids are rows
+        cn.s_ext = __fadd_rn(ps2, cn.score);
+        cn.s_new = __fadd_rn(__fadd_rn(ps1, ps2), cn.score);
+        cn.pad0 = cn.pad1 = cn.pad2 = 0;
+        out[k] = cn;
     }
     if (lane == 0) *out_n = nc;
     // the score sums the assembly needs per connection, here where 19 x n warps can fetch the peak scores in
@@ -792,7 +809,7 @@ cudaError_t launch_pair_sample_offsets(const ekp_peak* line, const int* part_off
 
 // Test hook: the device replay of libstdc++'s std::sort on caller-supplied scores (one block, as in
 // paf_connect_kernel), so that the tie permutation -- including the heapsort fallback, which real scenes never
-// reach -- can be compared with the compiled reference's std::sort.  scratch: n + 2 * replay_queue_cap words.
+// reach -- can be compared with the compiled reference's std::sort.  scratch: 2 n + 2 * replay_queue_cap words.
 constexpr int kDebugSortThreads = 256;
 __global__ void __launch_bounds__(kDebugSortThreads) debug_std_sort_kernel(float* scores, unsigned* tags, int n, unsigned* scratch) {
     __shared__ int ctl[4];
@@ -801,12 +818,13 @@ __global__ void __launch_bounds__(kDebugSortThreads) debug_std_sort_kernel(float
     ReplayWork W;
     W.cap = replay_queue_cap(n, kDebugSortThreads);
     W.blocks = scratch;
-    W.range = scratch + n;
+    W.tmp = scratch + n;
+    W.range = W.tmp + n;
     W.depth = W.range + W.cap;
     W.ctl = ctl;
     std_sort_desc_block(A, n, W);
 }
-size_t debug_std_sort_scratch_words(int n) { return (size_t) n + 2 * (size_t) replay_queue_cap(n, kDebugSortThreads); }
+size_t debug_std_sort_scratch_words(int n) { return 2 * (size_t) n + 2 * (size_t) replay_queue_cap(n, kDebugSortThreads); }
 cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned* scratch, cudaStream_t stream) {
     debug_std_sort_kernel<<<1, kDebugSortThreads, 0, stream>>>(scores, tags, n, scratch);
     return cudaGetLastError();
