@@ -213,6 +213,7 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     *out = nullptr;
     if (max_part <= 0) max_part = EKP_MAX_PART;
     if (max_cand <= 0) max_cand = EKP_MAX_CAND;
+    max_cand = (max_cand + 3) & ~3;  // the candidate arrays are read 16 bytes at a time
     if (max_batch < 1 || max_batch > 65535 || max_h < 5 || max_w < 5 || max_peaks < 1 || max_humans < 1 || max_peaks > EKP_LIMIT_PEAKS ||
         max_humans > EKP_LIMIT_HUMANS || max_part < 1 || max_part > EKP_LIMIT_PART || max_cand < 64 || max_cand > EKP_LIMIT_CAND)
         return fail(EKP_ERR_ARG, "ekp_create: bad capacity (batch %d <= 65535, map %dx%d >= 5x5, peaks %d <= %d, humans %d <= %d, "

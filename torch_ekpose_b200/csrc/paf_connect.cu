@@ -607,7 +607,7 @@ __device__ __forceinline__ int score_all_pairs(const PafSource& paf, const float
 // [sScore, sTag, sScore2, sTag2: max_cand words each].  max_part / max_cand are capacities of the context
 // (ekp_create_ex), reported through EKP_OVF_PART / EKP_OVF_CANDIDATES when a scene exceeds them.
 size_t connect_smem_bytes(int max_part, int max_cand, int plane_elems) {
-    return sizeof(float2) * (size_t) plane_elems + 2 * sizeof(ekp_peak) * (size_t) max_part + 4 * sizeof(float) * (size_t) max_cand;
+    return sizeof(float2) * (size_t) ((plane_elems + 1) & ~1) + 2 * sizeof(ekp_peak) * (size_t) max_part + 4 * sizeof(float) * (size_t) max_cand;
 }
 
 template <int kSrc, int kT>
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) 
     const PafSource& paf = P.paf;
     const int max_part = P.max_part, max_cand = P.max_cand;
     float2* sPlane = reinterpret_cast<float2*>(conn_smem);
-    ekp_peak* sA = reinterpret_cast<ekp_peak*>(sPlane + (kSrc == SRC_SMEM_PLANES ? paf.h * paf.w : 0));
+    ekp_peak* sA = reinterpret_cast<ekp_peak*>(sPlane + (kSrc == SRC_SMEM_PLANES ? (paf.h * paf.w + 1) & ~1 : 0));  // 16-byte aligned
     ekp_peak* sB = sA + max_part;
     float* sScore = reinterpret_cast<float*>(sB + max_part);
     unsigned* sTag = reinterpret_cast<unsigned*>(sScore + max_cand);
@@ -683,7 +683,16 @@ __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) 
         const float s = sScore[i];
         int rank = 0;
         bool tie = false;
-        for (int j = 0; j < n; j++) {
+        const int n4 = n & ~3;
+        for (int j = 0; j < n4; j += 4) {   // four candidates per shared-memory load (sScore is 16-byte aligned)
+            const float4 v = *reinterpret_cast<const float4*>(sScore + j);
+            rank += (v.x > s) || (v.x == s && j < i);
+            rank += (v.y > s) || (v.y == s && j + 1 < i);
+            rank += (v.z > s) || (v.z == s && j + 2 < i);
+            rank += (v.w > s) || (v.w == s && j + 3 < i);
+            tie |= (v.x == s && j != i) || (v.y == s && j + 1 != i) || (v.z == s && j + 2 != i) || (v.w == s && j + 3 != i);
+        }
+        for (int j = n4; j < n; j++) {
             const float sj = sScore[j];
             rank += (sj > s) || (sj == s && j < i);
             tie |= (sj == s) && (j != i);
@@ -849,6 +858,7 @@ static cudaError_t launch_one(const ConnectParams& P, int n, size_t smem, cudaSt
 }
 template <int kSrc>
 static cudaError_t launch_src(const ConnectParams& P, int n, size_t smem, int threads, cudaStream_t stream) {
+    if (threads == 1024) { if (kSrc == SRC_SMEM_PLANES) return launch_one<SRC_SMEM_PLANES, 1024>(P, n, smem, stream); threads = 512; }
     if (threads == 512) return launch_one<kSrc, 512>(P, n, smem, stream);
     if (threads == 256) return launch_one<kSrc, 256>(P, n, smem, stream);
     return launch_one<kSrc, 128>(P, n, smem, stream);
@@ -863,7 +873,7 @@ cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w) 
 #define EKP_RAISE(S, T) if (e == cudaSuccess) e = raise_dynamic_smem_limit(paf_connect_kernel<S, T>, big)
     EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256); EKP_RAISE(SRC_GLOBAL, 512);
     EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256); EKP_RAISE(SRC_GLOBAL_VEC2, 512);
-    EKP_RAISE(SRC_SMEM_PLANES, 128); EKP_RAISE(SRC_SMEM_PLANES, 256); EKP_RAISE(SRC_SMEM_PLANES, 512);
+    EKP_RAISE(SRC_SMEM_PLANES, 128); EKP_RAISE(SRC_SMEM_PLANES, 256); EKP_RAISE(SRC_SMEM_PLANES, 512); EKP_RAISE(SRC_SMEM_PLANES, 1024);
 #undef EKP_RAISE
     return e;
 }
@@ -878,7 +888,10 @@ cudaError_t launch_paf_connect(const ConnectParams& P_in, int n, cudaStream_t st
     const size_t smem = connect_smem_bytes(P.max_part, P.max_cand, staged ? paf.h * paf.w : 0);
     const int blocks = EKP_NUM_LIMB * n;
     int threads = blocks <= 4 * sms ? 2 * kConnThreads : kConnThreads;
-    if (staged && smem > 64 * 1024 && blocks <= 4 * sms) threads = 512;
+    if (staged && smem > 64 * 1024 && blocks <= 4 * sms) {
+        static const int env_big = getenv("EKP_CONN_BIG_THREADS") ? atoi(getenv("EKP_CONN_BIG_THREADS")) : 512;
+        threads = env_big;   // one block per SM: every thread it has goes to this limb
+    }
     // per-block regimes (same results in all of them): up to six rounds of ten-lanes-per-pair scoring straight from L2,
     // beyond that one thread per pair in two exact passes, on planes staged in shared memory where the launch has them
     static const int env_by_sample = getenv("EKP_BY_SAMPLE_MAX_PAIRS") ? atoi(getenv("EKP_BY_SAMPLE_MAX_PAIRS")) : -1;
