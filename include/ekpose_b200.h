@@ -197,9 +197,10 @@ int ekp_host_free(void *p);
  * pafmap [f1,f2,f3].  Runs on the device selected by EKP_DEVICE (default 0).  Unlike the
  * reference (always 0, undefined behaviour on bad input) a negative ekp_status is returned
  * when the input is invalid or no GPU is available.
- * Only what stage 4 reads of pafmap crosses the bus: a kernel lists the <= 10 sample positions of every
- * candidate pair, the two floats at each position are gathered from the caller's array and uploaded
- * (environment EKP_PROCESS_PAF_UPLOAD=dense uploads the whole tensor instead). */
+ * Only what stage 4 reads of pafmap crosses the bus: the <= 10 sample positions of every candidate pair are listed
+ * (on the host for up to 64 Ki samples: one upload, one download, no wait in between; by a kernel beyond that), the two
+ * floats at each position are gathered from the caller's array and uploaded.  Environment EKP_PROCESS_PAF_UPLOAD =
+ * listed (default) | sparse (always list on the device) | dense (upload the whole tensor). */
 int process_paf(int p1, int p2, int p3, float *peaks, int h1, int h2, int h3, float *heatmap, int f1, int f2,
                 int f3, float *pafmap);
 int get_num_humans(void);

@@ -66,7 +66,7 @@ def test_process_paf_known_answers(ek, case):
         assert n == 1 and float(scores[0]) == 1.5 and list(cids[0][1:5]) == [0, 1, 2, 3]
 
 
-@pytest.mark.parametrize("upload", ["sparse", "dense"])
+@pytest.mark.parametrize("upload", ["listed", "sparse", "dense"])
 @pytest.mark.parametrize("scene", util.SCENES)
 def test_process_paf_golden(ek, scene, upload, monkeypatch):
     """Reference peaks + nearest-upsampled PAF in, the compiled reference's subset out (bit-exact), both when

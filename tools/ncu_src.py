@@ -1,7 +1,7 @@
 """Per-source-line summary of a kernel in an .ncu-rep (needs `--import-source on` at capture time and -lineinfo):
 reads ncu's own CUDA/SASS correlation (`--page source --print-source cuda,sass`), so template instantiations
 and inlined device functions are attributed correctly.
-usage: python tools/ncu_src.py report.ncu-rep kernel_regex [top_n] [launch_index]"""
+usage: python tools/ncu_src.py report.ncu-rep|export.csv.gz kernel_regex [top_n] [launch_index]"""
 import collections
 import csv
 import os
@@ -11,8 +11,13 @@ import sys
 rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "-k", f"regex:{kname}"],
-                     capture_output=True, text=True).stdout
+if rep.endswith(".csv.gz") or rep.endswith(".csv"):   # an export made on the GPU box: ncu -i X --page source --print-source cuda,sass --csv
+    import gzip
+    import re
+    out = (gzip.open(rep, "rt") if rep.endswith(".gz") else open(rep)).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "-k", f"regex:{kname}"],
+                         capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 # the output is a sequence of (File Path, Function Name, header, rows...) blocks: one per source file and launch
 launches = collections.OrderedDict()
@@ -36,7 +41,7 @@ for r in rows:
     if hdr is None or not r[0].strip().isdigit():
         continue   # SASS rows and "..." rows
     launches[(cur_fn, seen[(cur_fn, cur_file)] - 1)].append((cur_file, hdr, r))
-fns = sorted({k[0] for k in launches})
+fns = sorted({k[0] for k in launches if __import__("re").search(kname, k[0])})
 for fn in fns:
     items = launches.get((fn, which)) or []
     if not items:

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <mutex>
@@ -20,6 +21,7 @@ namespace ekp {
 size_t dense_frontend_smem_bytes(int tile_wl, bool materialise);
 int dense_frontend_tile_wl(int w);
 cudaError_t configure_dense_frontend();
+cudaError_t configure_dense_plane(int max_h, int max_w);
 cudaError_t set_interior_taps(const float* taps64);
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream);
 cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream);
@@ -27,6 +29,9 @@ cudaError_t launch_upsample_nearest(const float* lo, int layout, int n, int h, i
 cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fixed, int peaks_stride, int p3, int n, int W,
                                 int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow, cudaStream_t stream);
 cudaError_t configure_peaks_sort(int raw_cap);
+int peaks_one_max();
+cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, int p3, int W, int H, int raw_cap, int max_part, ekp_peak* line,
+                                         int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream);
 cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int max_part, int id_from_key, int n,
                               ekp_peak* line, int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
 cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w);
@@ -261,6 +266,7 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     e = cudaMemcpy(c->cubic, cubic, sizeof(cubic), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = configure_dense_frontend();
+    if (e == cudaSuccess) e = configure_dense_plane(max_h, max_w);
     if (e == cudaSuccess) {  // taps of interior rows/columns depend only on the phase (D & 7): constant memory
         std::vector<float> t8;
         build_dense_taps(8, t8);
@@ -798,6 +804,142 @@ int compat_ctx(int need_peaks, int need_humans, int need_part, int need_cand) {
 }
 }  // namespace
 
+// ---- process_paf, small scenes: everything stage 4 needs in ONE upload, no mid-call synchronisation ---------------
+// For up to kListedMaxSamples samples the host lists them itself: it buckets the caller's peaks by part (the order of
+// the reference's own buckets, pafprocess.cpp:24-43), walks the pairs of every limb in the kernel's order (a outer,
+// b inner) and copies the two floats at each of the <= 10 sample positions out of the caller's paf_mat -- the positions
+// by the roundpaf arithmetic of pafprocess.cpp:228-233, 240-242, which is index arithmetic on the INPUT, not scoring:
+// unit vectors, dot products, both criteria, sort, assignment and assembly all run in the kernels, on these values.
+// One pinned block [pair prefix | peaks | samples] -> one H2D copy -> ingest, sort, connect (PAF_PACKED), assemble ->
+// one D2H copy of the result record -> one wait.  The part-sorted peak table the getters index (pafprocess.cpp:208-218)
+// is the bucket order itself, so it never has to come back from the device.
+// Returns 1 when the scene is not eligible (an invalid peak, a part over max_part, too many samples): the general path
+// below then runs and reports whatever is wrong.
+namespace {
+const long long kListedMaxSamples = 64 * 1024;
+unsigned char* g_listed_host = nullptr; unsigned char* g_listed_dev = nullptr; size_t g_listed_cap = 0;
+const int kHostPairs[EKP_NUM_LIMB][2] = {{1, 2}, {1, 5}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {1, 8}, {8, 9}, {9, 10}, {1, 11},
+                                         {11, 12}, {12, 13}, {1, 0}, {0, 14}, {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17}};
+const int kHostPairsNet[EKP_NUM_LIMB] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 28, 30, 34, 32, 36, 18, 26};  // x channel; y = x + 1
+
+static double now_us() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+int process_paf_listed(ekp_ctx* c, long long npk, int p3, const float* peaks, int h1, int f1, int f2, int f3, const float* pafmap,
+                       unsigned* ovf_out) {
+    static const bool trace = getenv("EKP_TRACE_PROCESS_PAF") != nullptr;   // phase times on stderr (tools/compat_latency.py)
+    const double t0 = trace ? now_us() : 0.0;
+    std::vector<int> bucket[EKP_NUM_PART];
+    for (long long k = 0; k < npk; k++) {
+        const float* row = peaks + k * p3;
+        const float pt = row[4];
+        const int part = pt > -1.f && pt < (float) EKP_NUM_PART ? (int) pt : -1;
+        const int x = (int) row[0], y = (int) row[1];   // C truncation, pafprocess.cpp:30-31
+        if (part < 0 || !(row[0] > -1.f && row[0] < (float) f2 + 1.f) || !(row[1] > -1.f && row[1] < (float) f1 + 1.f) || x < 0 || x >= f2 ||
+            y < 0 || y >= f1 || !(row[2] == row[2]))
+            return 1;
+        bucket[part].push_back((int) k);
+    }
+    int pair_base[32] = {0};
+    long long acc = 0;
+    for (int l = 0; l < EKP_NUM_LIMB; l++) {
+        const size_t nA = bucket[kHostPairs[l][0]].size(), nB = bucket[kHostPairs[l][1]].size();
+        if (nA > (size_t) c->max_part || nB > (size_t) c->max_part) return 1;
+        pair_base[l] = (int) acc;
+        acc += (long long) nA * (long long) nB;
+    }
+    pair_base[EKP_NUM_LIMB] = (int) acc;
+    const long long nsamples = acc * 10;
+    if (nsamples > kListedMaxSamples) return 1;
+    const size_t off_peaks = sizeof(pair_base), off_samp = (off_peaks + sizeof(float) * (size_t) npk * p3 + 7) & ~(size_t) 7;
+    const size_t bytes = off_samp + sizeof(float2) * (size_t) (nsamples > 0 ? nsamples : 1);
+    if (g_listed_cap < bytes) {
+        if (g_listed_host) cudaFreeHost(g_listed_host);
+        if (g_listed_dev) cudaFree(g_listed_dev);
+        g_listed_host = nullptr; g_listed_dev = nullptr; g_listed_cap = 0;
+        const size_t cap = bytes + bytes / 2 + 4096;
+        CU(cudaMallocHost((void**) &g_listed_host, cap));
+        CU(cudaMalloc((void**) &g_listed_dev, cap));
+        g_listed_cap = cap;
+    }
+    memcpy(g_listed_host, pair_base, sizeof(pair_base));
+    memcpy(g_listed_host + off_peaks, peaks, sizeof(float) * (size_t) npk * p3);
+    float2* samp = reinterpret_cast<float2*>(g_listed_host + off_samp);
+    size_t k = 0;
+    for (int l = 0; l < EKP_NUM_LIMB; l++) {
+        const std::vector<int>& A = bucket[kHostPairs[l][0]];
+        const std::vector<int>& B = bucket[kHostPairs[l][1]];
+        const float* chan = pafmap + kHostPairsNet[l];
+        for (int ia : A) {
+            const int ax = (int) peaks[(size_t) ia * p3], ay = (int) peaks[(size_t) ia * p3 + 1];
+            for (int ib : B) {
+                const int bx = (int) peaks[(size_t) ib * p3], by = (int) peaks[(size_t) ib * p3 + 1];
+                volatile float step_x = (float) (bx - ax) / 10.0f, step_y = (float) (by - ay) / 10.0f;   // pafprocess.cpp:224-225
+                for (int i = 0; i < 10; i++) {
+                    volatile float fx = (float) i * step_x, fy = (float) i * step_y;   // float products, then float sums (:228),
+                    volatile float sx = (float) ax + fx, sy = (float) ay + fy;         // rounded one by one like the C++ (no contraction)
+                    int lx = (int) ((double) sx + 0.5), ly = (int) ((double) sy + 0.5);  // roundpaf, :240-242
+                    lx = std::min(std::max(lx, 0), f2 - 1);
+                    ly = std::min(std::max(ly, 0), f1 - 1);
+                    const float* q = chan + ((size_t) ly * f2 + lx) * f3;
+                    samp[k++] = make_float2(q[0], q[1]);
+                }
+            }
+        }
+    }
+    const double t1 = trace ? now_us() : 0.0;
+    cudaStream_t st = nullptr;
+    if (c->has_run && c->last_stream != st) CU(cudaStreamWaitEvent(st, c->done, 0));
+    CU(cudaMemcpyAsync(g_listed_dev, g_listed_host, bytes, cudaMemcpyHostToDevice, st));
+    mark(c, 0, st);
+    mark(c, 1, st);
+    int rc = EKP_OK;
+    if (npk <= peaks_one_max()) {   // ingest + sort in one block, no counters to clear
+        CU(launch_peaks_ingest_sort_one(reinterpret_cast<const float*>(g_listed_dev + off_peaks), (int) npk, p3, f2, f1, c->max_peaks, c->max_part,
+                                        c->line, c->part_off, c->n_peaks, c->raw_count, c->overflow, st));
+        c->launches += 1;
+    } else {
+        CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+        CU(launch_peaks_ingest(reinterpret_cast<const float*>(g_listed_dev + off_peaks), nullptr, (int) npk, (int) npk, p3, 1, f2, f1, c->raw,
+                               c->raw_count, c->max_peaks, c->overflow, st));
+        c->launches += 1;
+        rc = run_peak_sort(c, 1, /*id_from_key=*/1, st);
+        if (rc) return rc;
+    }
+    PafSource src;
+    src.layout = EKP_LAYOUT_NHWC; src.H = f1; src.W = f2; src.C = f3; src.h = f1 / 8; src.w = f2 / 8; src.ids_are_rows = 0;
+    src.ptr = reinterpret_cast<const float*>(g_listed_dev + off_samp); src.mode = PAF_PACKED;
+    src.pair_base = reinterpret_cast<const int*>(g_listed_dev);
+    rc = run_connect_assemble(c, 1, src, h1, st);
+    if (rc) return rc;
+    rc = finish_submit(c, 1, st);
+    if (rc) return rc;
+    const double t2 = trace ? now_us() : 0.0;
+    std::vector<float> subset((size_t) c->max_humans * 20);
+    int nh = 0, np = 0;
+    rc = ekp_results(c, &nh, subset.data(), &np, nullptr, ovf_out);
+    if (rc) return rc;
+    if (trace) fprintf(stderr, "process_paf listed: %lld peaks %lld samples | host listing %.1f us, submit %.1f us, wait + results %.1f us\n", npk,
+                       nsamples, t1 - t0, t2 - t1, now_us() - t2);
+    g_num_humans = nh;
+    g_subset.assign(subset.begin(), subset.begin() + (size_t) nh * 20);
+    const float* hs = reinterpret_cast<const float*>(c->h_records + c->lay.off_hscore);
+    g_hscore.assign(hs, hs + nh);
+    g_line.clear();
+    g_line.reserve((size_t) npk);
+    for (int part = 0; part < EKP_NUM_PART; part++)   // peak_infos_line: the buckets one after the other (pafprocess.cpp:38-43)
+        for (int kk : bucket[part]) {
+            const float* row = peaks + (size_t) kk * p3;
+            ekp_peak pk;
+            pk.x = (int) row[0]; pk.y = (int) row[1]; pk.score = row[2]; pk.id = kk;
+            g_line.push_back(pk);
+        }
+    return EKP_OK;
+}
+}  // namespace
+
 extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, float* heatmap, int f1, int f2,
                            int f3, float* pafmap) {
     (void) h2; (void) h3; (void) heatmap;  // heat_mat is used only through h1 (pafprocess.cpp:83)
@@ -819,6 +961,20 @@ extern "C" int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2,
             CU(cudaMalloc((void**) &g_dev_peaks, pk_elems * sizeof(float))); g_dev_peaks_cap = pk_elems; }
         cudaStream_t st = nullptr;
         const int npk_i = (int) npk;
+        const char* upload_mode = getenv("EKP_PROCESS_PAF_UPLOAD");   // unset or "listed": the small-scene path first
+        if ((!upload_mode || strcmp(upload_mode, "listed") == 0) && paf_elems < (1ull << 32)) {
+            unsigned ovf = 0;
+            rc = process_paf_listed(c, npk, p3, peaks, h1, f1, f2, f3, pafmap, &ovf);
+            if (rc == EKP_OK) return EKP_OK;
+            if (rc == EKP_ERR_CAPACITY && !(ovf & (EKP_OVF_PEAKS | EKP_OVF_BADPEAK))) {
+                bool grew = false, stuck = false;
+                if (ovf & EKP_OVF_HUMANS) { if (c->max_humans < EKP_LIMIT_HUMANS) { need_humans = std::min(c->max_humans * 4, EKP_LIMIT_HUMANS); grew = true; } else stuck = true; }
+                if (ovf & EKP_OVF_PART) { if (c->max_part < EKP_LIMIT_PART) { need_part = std::min(c->max_part * 4, EKP_LIMIT_PART); grew = true; } else stuck = true; }
+                if (ovf & EKP_OVF_CANDIDATES) { if (c->max_cand < EKP_LIMIT_CAND) { need_cand = std::min(c->max_cand * 4, EKP_LIMIT_CAND); grew = true; } else stuck = true; }
+                if (grew && !stuck) continue;
+            }
+            if (rc != 1) return rc;
+        }
         // Sparse upload (default): stage 4 reads at most 10 positions of paf_mat per candidate pair, a few KB
         // against the 24 MB tensor.  Pairs per limb follow from the part column of the caller's peaks.
         int pair_base[EKP_NUM_LIMB + 1];

@@ -33,6 +33,8 @@
 //
 // History (profiles/README.md): issue-slot bound at 0.50 of the measured HBM roofline (666 M warp
 // instructions) -> per-thread streaming stores at 0.92 (145 M) -> TMA bulk stores + warp roles 0.94.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -449,33 +451,28 @@ __device__ __forceinline__ void build_task_list(const DenseParams& p, const Tile
     }
 }
 
-// One (part, 30-column strip) task, by one warp: smoothed map of the tile's rows (+ one halo row above and
-// below) in registers, 3x3 max NMS, peaks appended to the image's raw list.
-template <bool kDebug>
-__device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g, const float* sHeat, const float* sTaps, int task) {
+// One (part, 30-column strip, <= kTaskTB row blocks) task, by one warp: smoothed map of the task's rows (+ one halo row
+// above and below) in registers, 3x3 max NMS, peaks appended to the image's raw list.  The staged stride-8 samples of
+// part c are at base[j * rstride + i * CS] (row j, column i of the whole map): CS = 19 for the HWC tile patch of the
+// tiled kernels, 1 for the plane of the plane kernel.  X0 / TW: first full-resolution column / width the task's strips
+// tile; m0 / tb: first stride-8 row block / number of row blocks.
+template <bool kDebug, int CS>
+__device__ __forceinline__ void nms_task_at(const DenseParams& p, int img, int c, int strip, int m0, int tb, int X0, int TW,
+                                            const float* __restrict__ base, int rstride, const float* __restrict__ sTaps) {
     const int h = p.h, w = p.w, H = 8 * h, W = 8 * w;
-    const int hcols = p.tile_wl + 6;
     const int lane = threadIdx.x & 31;
-    const int TW = 8 * g.twl, X0 = 8 * g.i0;
-    const int nstrips = (TW + 29) / 30;
-    const int sub = task >= EKP_NUM_PART * nstrips ? task / (EKP_NUM_PART * nstrips) : 0;
-    task -= sub * (EKP_NUM_PART * nstrips);
-    const int img = g.img, m0 = g.m0 + sub * kTaskTB, tb = min(kTaskTB, g.m0 + g.tb - m0);  // rows of this sub-tile
     const float NEG_INF = __int_as_float(0xff800000);
-    const int rstride = hcols * EKP_HEAT_CH;
     PeakSink sink;
     sink.raw = p.raw + (size_t) img * p.raw_cap;
     sink.count = p.raw_count + img;
     sink.cap = p.raw_cap;
 
-    const int c = (int) fastdiv(task, magic_of(nstrips));
-    const int strip = task - c * nstrips;
     const int X = X0 - 1 + 30 * strip + lane;
     const bool inb = X >= 0 && X < W;
     const bool out_lane = lane >= 1 && lane <= 30 && X < X0 + TW && X < W;
     const int Xc = min(max(X, 0), min(W - 1, X0 + TW));  // lanes past the halo are never outputs
     const int bx = min(max((Xc >> 3) - 2, 0), w - 5);
-    const float* colp = sHeat + (bx - g.hc0) * EKP_HEAT_CH + c - g.hr0 * rstride;
+    const float* colp = base + bx * CS;
 
     // horizontal taps of this lane's column (only now: a skipped strip must not pay for the loads);
     // interior columns take them from the phase table in shared memory, border columns from global
@@ -491,10 +488,10 @@ __device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g
     auto trow = [&](int j) -> float {  // horizontal 5-tap pass on stride-8 row j
         const float* s = colp + j * rstride;
         float acc = __fmul_rn(axv.x, s[0]);
-        acc = fmaf(axv.y, s[EKP_HEAT_CH], acc);
-        acc = fmaf(axv.z, s[2 * EKP_HEAT_CH], acc);
-        acc = fmaf(axv.w, s[3 * EKP_HEAT_CH], acc);
-        acc = fmaf(ax4, s[4 * EKP_HEAT_CH], acc);
+        acc = fmaf(axv.y, s[CS], acc);
+        acc = fmaf(axv.z, s[2 * CS], acc);
+        acc = fmaf(axv.w, s[3 * CS], acc);
+        acc = fmaf(ax4, s[4 * CS], acc);
         return acc;
     };
     float T0 = 0.f, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f;
@@ -523,11 +520,11 @@ __device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g
     NmsState st;
     st.hm2 = NEG_INF; st.hm1 = NEG_INF; st.s1 = NEG_INF;
     const int Ytop = 8 * m0 - 1;
-    if (Ytop >= 0) {  // halo row above the tile: contributes its horizontal max only
+    if (Ytop >= 0) {  // halo row above the task's rows: contributes its horizontal max only
         window(m0 - 1);
         const float acc = row_generic(Ytop);
         nms_row(st, inb ? acc : NEG_INF, X, Ytop, false, p.thr, c, sink);
-        st.s1 = NEG_INF;  // not a tile-owned row: never reported from here
+        st.s1 = NEG_INF;  // not an owned row: never reported from here
     }
     for (int b = 0; b < tb; b++) {
         const int m = m0 + b;
@@ -552,7 +549,7 @@ __device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g
             }
         }
     }
-    const int Ybot = 8 * (m0 + tb);  // halo row below the tile (or the virtual row below the image)
+    const int Ybot = 8 * (m0 + tb);  // halo row below (or the virtual row below the image)
     float sb = NEG_INF;
     if (Ybot < H) {
         window(m0 + tb);
@@ -560,6 +557,21 @@ __device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g
         if (inb) sb = acc;
     }
     nms_row(st, sb, X, Ybot, out_lane, p.thr, c, sink);
+}
+
+// ... of a tile of the tiled kernels: task = (sub-tile, part, strip), samples in the tile's HWC patch
+template <bool kDebug>
+__device__ __forceinline__ void nms_task(const DenseParams& p, const TileGeom& g, const float* sHeat, const float* sTaps, int task) {
+    const int hcols = p.tile_wl + 6;
+    const int TW = 8 * g.twl, X0 = 8 * g.i0;
+    const int nstrips = (TW + 29) / 30;
+    const int sub = task >= EKP_NUM_PART * nstrips ? task / (EKP_NUM_PART * nstrips) : 0;
+    task -= sub * (EKP_NUM_PART * nstrips);
+    const int m0 = g.m0 + sub * kTaskTB, tb = min(kTaskTB, g.m0 + g.tb - m0);  // rows of this sub-tile
+    const int rstride = hcols * EKP_HEAT_CH;
+    const int c = (int) fastdiv(task, magic_of(nstrips));
+    const int strip = task - c * nstrips;
+    nms_task_at<kDebug, EKP_HEAT_CH>(p, g.img, c, strip, m0, tb, X0, TW, sHeat + c - g.hr0 * rstride - g.hc0 * EKP_HEAT_CH, rstride, sTaps);
 }
 
 // The calling warp takes surviving NMS tasks from the tile's list until none is left.
@@ -689,6 +701,147 @@ dense_frontend_kernel(const DenseParams p) {
     else process_tile_lean<kDebug>(p, g, sm, ctl);
 }
 
+// ---- the plane kernel: stages 1-3 without materialisation for the network's own layout (NCHW) ----------------------
+// One CTA per (part, image).  In NCHW a part's stride-8 map is ONE contiguous plane of h*w floats (10-60 KB at the
+// BASELINE shapes): the TMA engine brings it into shared memory with a single bulk copy (cp.async.bulk global ->
+// shared, completion on an mbarrier) -- no halo re-staging (the tiled kernel stages every sample ~4.9 times), no index
+// arithmetic, no transposition.  Then, per CTA:
+//   * a table M[row][strip] = max(0, maximum of the stride-8 row over the <= 9 columns a 30-column strip can touch);
+//   * the exact early-out of build_task_list per (row-block pair, strip) task from 5 table entries per row block;
+//   * the surviving tasks run nms_task_at on the plane (column stride 1), pulled from a list by the CTA's warps.
+// Same arithmetic, same peaks as the tiled kernels (tests/test_gpu_parity.py); 43 M -> ~21 M warp instructions on the
+// 64 x 368x432 batch (the tiled kernel spent ~60 % of its instructions on staging and the early-out tables).
+constexpr int kPlaneThreads = 256;
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned) __cvta_generic_to_shared(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned) __cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// A plane may be cut into `slices` groups of row-block pairs (blockIdx.z), each staging only its rows + halo -- still
+// one contiguous range of the plane -- so that a small batch of big maps fills the GPU (16 x 1312x736: 288 -> 864 CTAs).
+__host__ __device__ inline int plane_pairs(int h) { return (h + kTaskTB - 1) / kTaskTB; }
+__host__ __device__ inline void plane_slice_rows(int h, int slices, int slice, int& rp_lo, int& rp_hi, int& r_lo, int& r_hi) {
+    const int nrp = plane_pairs(h);
+    rp_lo = (int) ((long long) nrp * slice / slices);
+    rp_hi = (int) ((long long) nrp * (slice + 1) / slices);
+    const int m0 = rp_lo * kTaskTB, m1 = min(rp_hi * kTaskTB, h);   // row blocks [m0, m1)
+    r_lo = max(min(m0 - 3, h - 5), 0);                             // staged rows: the windows of the rows and their halo rows
+    r_hi = min(max(m1 + 2, 4), h - 1);
+}
+static size_t plane_smem_bytes(int h, int w, int slices) {
+    const int nstrips = (8 * w + 29) / 30;
+    int rows = 0, pairs = 0;
+    for (int sl = 0; sl < slices; sl++) {
+        int a, b, r0, r1;
+        plane_slice_rows(h, slices, sl, a, b, r0, r1);
+        rows = r1 - r0 + 1 > rows ? r1 - r0 + 1 : rows;
+        pairs = b - a > pairs ? b - a : pairs;
+    }
+    size_t bytes = sizeof(float) * (size_t) ((rows * w + 3) & ~3);     // the staged rows of the plane
+    bytes += sizeof(float) * (size_t) rows * nstrips;                  // M[row][strip]
+    bytes += sizeof(unsigned short) * (size_t) ((pairs * nstrips + 1) & ~1);  // surviving tasks
+    return bytes;
+}
+
+__global__ void __launch_bounds__(kPlaneThreads) dense_plane_kernel(const DenseParams p, int slices) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) float sTaps[64];
+    __shared__ __align__(8) unsigned long long sBar;
+    __shared__ int sNumActive, sNextTask;
+    const int c = blockIdx.x, img = blockIdx.y;
+    const int h = p.h, w = p.w, W = 8 * w;
+    const int nstrips = (W + 29) / 30;
+    int rp_lo, rp_hi, r_lo, r_hi;
+    plane_slice_rows(h, slices, blockIdx.z, rp_lo, rp_hi, r_lo, r_hi);
+    const int nrows = r_hi - r_lo + 1, nel = nrows * w, ntask = (rp_hi - rp_lo) * nstrips;
+    float* sRows = smem;
+    float* sM = sRows + ((nel + 3) & ~3);
+    unsigned short* sList = reinterpret_cast<unsigned short*>(sM + nrows * nstrips);
+    const float* src = p.heat + ((size_t) img * EKP_HEAT_CH + c) * h * w + (size_t) r_lo * w;
+    const bool bulk = (nel & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;  // 16-byte aligned source and size
+    if (threadIdx.x == 0) {
+        sNumActive = 0; sNextTask = 0;
+        if (bulk) mbar_init(&sBar, 1);
+    }
+    if (threadIdx.x < 64) sTaps[threadIdx.x] = cTapsInterior[threadIdx.x >> 3][threadIdx.x & 7];
+    if (bulk) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&sBar, (unsigned) nel * 4u);
+            bulk_load(sRows, src, (unsigned) nel * 4u, &sBar);
+        }
+        mbar_wait(&sBar, 0);
+    } else {
+        for (int i = threadIdx.x; i < nel; i += kPlaneThreads) sRows[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const float* base = sRows - r_lo * w;   // base[j * w + i] = sample (row j, column i) of the map, j in [r_lo, r_hi]
+    // M[r][s]: what row r can contribute to strip s at most (the columns a strip's lanes read: build_task_list)
+    for (int idx = threadIdx.x; idx < nrows * nstrips; idx += kPlaneThreads) {
+        const int r = idx / nstrips, strip = idx - r * nstrips;
+        const int Xa = -1 + 30 * strip;
+        const int xlo = min(max(Xa, 0), W - 1), xhi = min(max(Xa + 31, 0), W - 1);
+        const int c_lo = min(max((xlo >> 3) - 2, 0), w - 5), c_hi = min(max((xhi >> 3) - 2, 0), w - 5) + 4;
+        float mx = 0.f;
+        for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, sRows[r * w + i]);
+        sM[idx] = mx;
+    }
+    __syncthreads();
+    // exact early-out per (row-block pair, strip): same bounds as build_task_list
+    for (int t = threadIdx.x; t < ntask; t += kPlaneThreads) {
+        const int rp = rp_lo + t / nstrips, strip = t % nstrips;
+        const int b_lo = rp * kTaskTB, b_hi = min(b_lo + kTaskTB, h);
+        bool active = !(p.thr > 0.f);
+        for (int m = b_lo; m < b_hi && !active; m++) {
+            const int wb = min(max(m - 2, 0), h - 5);
+            const bool interior = m >= 2 && m <= h - 3;
+            float bound = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const float mj = sM[(wb + j - r_lo) * nstrips + strip];
+                bound = interior ? fmaf(cTapsInteriorMax[j], mj, bound) : fmaxf(bound, mj);
+            }
+            active = bound > p.thr * 0.9999f;
+        }
+        if (active) sList[atomicAdd(&sNumActive, 1)] = (unsigned short) t;
+    }
+    __syncthreads();
+    const int nactive = sNumActive;
+    for (;;) {
+        int item = 0;
+        if ((threadIdx.x & 31) == 0) item = atomicAdd(&sNextTask, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nactive) break;
+        const int t = sList[item];
+        const int rp = rp_lo + t / nstrips, strip = t % nstrips;
+        const int m0 = rp * kTaskTB;
+        nms_task_at<false, 1>(p, img, c, strip, m0, min(kTaskTB, h - m0), 0, W, base, w, sTaps);
+    }
+}
+
 static size_t smem_bytes(int tile_wl, bool materialise, int tb) {
     size_t floats = (size_t) (tb + 6) * (tile_wl + 6) * EKP_HEAT_CH + (size_t) (tile_wl + 6) * EKP_HEAT_CH;
     if (!materialise) return sizeof(float) * floats;
@@ -711,10 +864,20 @@ cudaError_t configure_dense_frontend() {
     if (e == cudaSuccess) e = raise_dynamic_smem_limit(dense_frontend_kernel<false, true, kTB>, smem_bytes(kMaxTwl, false, kTB));
     return e;
 }
+// per context: the plane kernel's shared memory depends on the largest map the context takes
+constexpr size_t kPlaneSmemMax = 200 * 1024;
+cudaError_t configure_dense_plane(int max_h, int max_w) {
+    const size_t need = plane_smem_bytes(max_h, max_w, 1);
+    return raise_dynamic_smem_limit(dense_plane_kernel, need <= kPlaneSmemMax ? need : 48 * 1024);
+}
 
 // One CTA per tile.  (Persistent variants -- resident CTAs pulling tiles from a counter with the next tile's
 // patches prefetched into a second buffer -- were measured SLOWER on B200 twice: 0.442 vs 0.412 ms with
 // per-thread stores, 0.408 vs 0.381 ms with the bulk stores and warp roles; see profiles/README.md.)
+static bool lean_tiled_forced() {  // EKP_LEAN_TILED=1: the tiled lean kernel also for NCHW input (measurements)
+    static const bool v = getenv("EKP_LEAN_TILED") && atoi(getenv("EKP_LEAN_TILED")) != 0;
+    return v;
+}
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
     const unsigned gx = (p.w + p.tile_wl - 1) / p.tile_wl;
     auto grid = [&](int tb) { return dim3(gx, (p.h + tb - 1) / tb, p.n); };
@@ -722,8 +885,20 @@ cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream) {
         dense_frontend_kernel<false, true, kTB><<<grid(kTB), kLeanThreads, smem_bytes(p.tile_wl, false, kTB), stream>>>(p);
     } else if (p.paf_mat) {
         dense_frontend_kernel<true, false, kTB><<<grid(kTB), kMatThreads, smem_bytes(p.tile_wl, true, kTB), stream>>>(p);
+    } else if (p.layout == EKP_LAYOUT_NCHW && plane_smem_bytes(p.h, p.w, 1) <= kPlaneSmemMax && ((8 * p.w + 29) / 30) * plane_pairs(p.h) < 65536 &&
+               !lean_tiled_forced()) {
+        // Lean, NCHW (the network's layout): CTAs per (part, image[, slice of rows]) on the part's contiguous plane;
+        // a batch too small to give every SM a CTA (a single frame: 18 planes) is sliced until there are about two per SM
+        // (slicing a launch that already fills the GPU only adds halo rows: 16 x 1312x736 99 -> 107 us, measured)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int slices = EKP_NUM_PART * p.n >= sms ? 1 : (2 * sms + EKP_NUM_PART * p.n - 1) / (EKP_NUM_PART * p.n);
+        slices = slices < 1 ? 1 : (slices > plane_pairs(p.h) / 2 ? (plane_pairs(p.h) / 2 > 0 ? plane_pairs(p.h) / 2 : 1) : slices);
+        if (slices > 16) slices = 16;
+        dense_plane_kernel<<<dim3(EKP_NUM_PART, p.n, slices), kPlaneThreads, plane_smem_bytes(p.h, p.w, slices), stream>>>(p, slices);
     } else {
-        // Lean: 16-row tiles balance best while there are few of them; with many waves of tiles taller ones win (their
+        // Lean, other layouts / huge maps: 16-row tiles balance best while there are few of them; with many waves of tiles taller ones win (their
         // fixed cost -- staging a 6-row halo, the early-out tables -- is shared by twice the rows).  Same results either way.
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);

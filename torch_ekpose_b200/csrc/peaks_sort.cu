@@ -97,6 +97,79 @@ __global__ void __launch_bounds__(kSortThreads) peaks_sort_kernel(const RawPeak*
     if (ovf) atomicOr(overflow + img, ovf);
 }
 
+// ---- one image, process_paf's input format, ingest + sort in ONE block (the host-pointer operator surface) --------
+// peaks_ingest_kernel + peaks_sort_kernel for a single list of up to kOneMaxPeaks peaks without the intermediate
+// RawPeak list and without the memset of the counters: the block validates the rows, buckets the input indices by
+// part in shared memory, and writes every peak straight to its row of the part-sorted table (rank = part offset +
+// number of earlier peaks of the same part: the reference's bucket order, pafprocess.cpp:24-43).  It also (re)sets the
+// image's overflow word, so the call needs no cudaMemsetAsync in front.
+constexpr int kOneThreads = 256;
+constexpr int kOneMaxPeaks = 4096;
+__global__ void __launch_bounds__(kOneThreads) peaks_ingest_sort_one_kernel(const float* __restrict__ peaks, int npk, int p3, int W, int H,
+                                                                            int raw_cap, int max_part, ekp_peak* __restrict__ line,
+                                                                            int* __restrict__ part_off, int* __restrict__ n_peaks,
+                                                                            int* __restrict__ raw_count, unsigned* __restrict__ overflow) {
+    __shared__ unsigned short sKey[kOneMaxPeaks];   // input indices, bucketed by part
+    __shared__ unsigned char sPart[kOneMaxPeaks];
+    __shared__ int sCount[EKP_NUM_PART + 1], sBase[EKP_NUM_PART + 2], sFill[EKP_NUM_PART + 1];
+    __shared__ unsigned sOvf;
+    const int n = min(npk, min(raw_cap, kOneMaxPeaks));
+    if (threadIdx.x <= EKP_NUM_PART) { sCount[threadIdx.x] = 0; sFill[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) sOvf = npk > raw_cap ? EKP_OVF_PEAKS : 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += kOneThreads) {
+        const float* row = peaks + (size_t) k * p3;
+        const int x = (int) row[0], y = (int) row[1], part = (int) row[4];
+        const float sc = row[2];
+        int p = part;
+        if (part < 0 || part >= EKP_NUM_PART || x < 0 || x >= W || y < 0 || y >= H || !(sc == sc)) {
+            atomicOr(&sOvf, EKP_OVF_BADPEAK);  // the reference has undefined behaviour here; we refuse
+            p = EKP_NUM_PART;                  // sorted behind every real part, never used
+        }
+        sPart[k] = (unsigned char) p;
+        atomicAdd(&sCount[p], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int p = 0; p <= EKP_NUM_PART; p++) { sBase[p] = off; off += sCount[p]; }
+        sBase[EKP_NUM_PART + 1] = off;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += kOneThreads) sKey[sBase[sPart[k]] + atomicAdd(&sFill[sPart[k]], 1)] = (unsigned short) k;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += kOneThreads) {
+        const int p = sPart[k];
+        int rank = sBase[p];
+        for (int j = sBase[p]; j < sBase[p + 1]; j++) rank += sKey[j] < k;
+        const float* row = peaks + (size_t) k * p3;
+        ekp_peak out;
+        if (p < EKP_NUM_PART) { out.x = (int) row[0]; out.y = (int) row[1]; }
+        else { out.x = 0; out.y = 0; }
+        out.score = row[2];
+        out.id = k;   // ids follow input order (pafprocess.cpp:29)
+        line[rank] = out;
+    }
+    if (threadIdx.x != 0) return;
+    unsigned ovf = sOvf;
+    for (int p = 0; p < EKP_NUM_PART; p++) {
+        part_off[p] = sBase[p];
+        if (sCount[p] > max_part) ovf |= EKP_OVF_PART;
+    }
+    part_off[EKP_NUM_PART] = sBase[EKP_NUM_PART];
+    part_off[EKP_NUM_PART + 1] = n;
+    n_peaks[0] = sBase[EKP_NUM_PART];
+    raw_count[0] = npk;
+    overflow[0] = ovf;
+}
+int peaks_one_max() { return kOneMaxPeaks; }
+cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, int p3, int W, int H, int raw_cap, int max_part, ekp_peak* line,
+                                         int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream) {
+    peaks_ingest_sort_one_kernel<<<1, kOneThreads, 0, stream>>>(peaks, npk, p3, W, H, raw_cap, max_part, line, part_off, n_peaks, raw_count,
+                                                               overflow);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fixed, int peaks_stride, int p3, int n,
                                 int W, int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow,
                                 cudaStream_t stream) {
