@@ -120,6 +120,10 @@ struct ConnectParams {
     Conn* conns;               // [n][19][max_part]
     int* n_conns;              // [n][19]
     unsigned* overflow;
+    // fused assembly: the block that finishes an image's last limb runs assemble_image on it (assemble.cuh)
+    int fuse_assemble;
+    int* limb_done;            // [n] finished limb blocks per image; the assembling block resets its counter to 0
+    AsmParams assemble;
 };
 
 struct DenseParams {
