@@ -25,6 +25,8 @@ cudaError_t configure_dense_plane(int max_h, int max_w);
 cudaError_t set_interior_taps(const float* taps64);
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream);
 cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream);
+int ref_frontend_launches(int refine);
+cudaError_t configure_ref_frontend(int max_h, int max_w);
 cudaError_t launch_upsample_nearest(const float* lo, int layout, int n, int h, int w, int C, float* out, cudaStream_t stream);
 cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fixed, int peaks_stride, int p3, int n, int W,
                                 int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow, cudaStream_t stream);
@@ -34,7 +36,7 @@ cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, int p3, in
                                          int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream);
 cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int max_part, int id_from_key, int n,
                               ekp_peak* line, int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
-cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w, int max_humans, int max_peaks);
+cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w);
 cudaError_t launch_paf_connect(const ConnectParams& P, int n, cudaStream_t stream);
 cudaError_t configure_assemble(int max_humans, int max_peaks, int max_part);
 cudaError_t launch_assemble(AsmParams P, int n, cudaStream_t stream);
@@ -155,7 +157,6 @@ struct ekp_ctx {
     int* n_peaks = nullptr;         // [max_batch]
     Conn* conns = nullptr;          // [max_batch][19][max_part]
     int* n_conns = nullptr;         // [max_batch][19]
-    int* limb_done = nullptr;       // [max_batch] finished limb blocks per image (fused assembly; self-resetting)
     unsigned char* records = nullptr;  // [max_batch] packed result records (ResultLayout)
     ResultLayout lay = {};
     float* in_block = nullptr;      // staging for the host-buffer entry point: [heat | paf] of one batch, contiguous
@@ -196,7 +197,7 @@ static inline void mark(ekp_ctx* c, int k, cudaStream_t st) {
 static int ctx_free(ekp_ctx* c) {
     if (!c) return EKP_OK;
     cudaSetDevice(c->device);
-    void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->limb_done, c->records,
+    void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->records,
                    c->in_block, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic, c->prep_tab};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {c->h_records, c->h_line};
@@ -254,7 +255,6 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     DEV_ALLOC(c->n_peaks, sizeof(int) * B);
     DEV_ALLOC(c->conns, sizeof(Conn) * B * EKP_NUM_LIMB * max_part);
     DEV_ALLOC(c->n_conns, sizeof(int) * B * EKP_NUM_LIMB);
-    DEV_ALLOC(c->limb_done, sizeof(int) * B);
     c->lay.off_subset = 16;
     c->lay.off_hparts = c->lay.off_subset + sizeof(float) * 20 * (size_t) max_humans;
     c->lay.off_hscore = c->lay.off_hparts + sizeof(ekp_peak) * EKP_NUM_PART * (size_t) max_humans;
@@ -269,14 +269,14 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = configure_dense_frontend();
     if (e == cudaSuccess) e = configure_dense_plane(max_h, max_w);
+    if (e == cudaSuccess) e = configure_ref_frontend(max_h, max_w);
     if (e == cudaSuccess) {  // taps of interior rows/columns depend only on the phase (D & 7): constant memory
         std::vector<float> t8;
         build_dense_taps(8, t8);
         e = set_interior_taps(t8.data() + 16 * 8);
     }
     if (e == cudaSuccess) e = configure_peaks_sort(max_peaks);
-    if (e == cudaSuccess) e = configure_connect(max_part, max_cand, max_h, max_w, max_humans, max_peaks);
-    if (e == cudaSuccess) e = cudaMemset(c->limb_done, 0, sizeof(int) * B);
+    if (e == cudaSuccess) e = configure_connect(max_part, max_cand, max_h, max_w);
     if (e == cudaSuccess) e = configure_assemble(max_humans, max_peaks, max_part);
     if (e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "context setup: %s", cudaGetErrorString(e)); }
     *out = c;
@@ -356,22 +356,15 @@ static int run_connect_assemble(ekp_ctx* c, int n, const PafSource& paf, int h1,
     ap.line = c->line; ap.max_peaks = c->max_peaks; ap.n_peaks = c->n_peaks; ap.part_off = c->part_off; ap.conns = c->conns;
     ap.n_conns = c->n_conns; ap.max_part = c->max_part; ap.max_humans = c->max_humans; ap.conn_cap = 0; ap.overflow = c->overflow;
     ap.records = c->records; ap.lay = c->lay;
-    // EKP_FUSE_ASSEMBLE=1 runs the assembly inside the connect kernel (the block that finishes an image's last limb
-    // assembles it: no second launch).  Measured on B200 (profiles/README.md, round 2): no gain once a batch is one CUDA
-    // graph launch -- 98.9 vs 100.7 us (64 x 368x432), 211.9 vs 214.0 us (16 crowded 1312x736) -- and 3 % slower on
-    // 256 x 656x368 (the assembly's shared memory costs the connect blocks occupancy), so it stays off by default.
-    static const bool fuse_on = getenv("EKP_FUSE_ASSEMBLE") && atoi(getenv("EKP_FUSE_ASSEMBLE")) != 0;
-    const bool fused = fuse_on && !c->timing;
     ConnectParams cp;
     cp.line = c->line; cp.part_off = c->part_off; cp.max_peaks = c->max_peaks; cp.max_part = c->max_part; cp.max_cand = c->max_cand;
     cp.paf = paf; cp.h1 = h1; cp.conns = c->conns; cp.n_conns = c->n_conns; cp.overflow = c->overflow;
-    cp.fuse_assemble = fused ? 1 : 0; cp.limb_done = c->limb_done; cp.assemble = ap;
     CU(launch_paf_connect(cp, n, st));
     mark(c, 3, st);
-    if (!fused) { CU(launch_assemble(ap, n, st)); c->launches += 1; }
+    CU(launch_assemble(ap, n, st));
     mark(c, 4, st);
     if (c->timing) c->timed_runs++;
-    c->launches += 1;
+    c->launches += 2;
     CU(cudaMemcpyAsync(c->h_records, c->records, c->lay.stride * (size_t) n, cudaMemcpyDeviceToHost, st));  // one packed copy
     return EKP_OK;
 }
@@ -428,7 +421,7 @@ static int enqueue_batch(ekp_ctx* c, const PostArgs& a, cudaStream_t st, int* ke
         p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.cubic = c->cubic;
         p.refine = a.frontend == EKP_FRONTEND_REFERENCE ? 1 : 0;
         CU(launch_ref_frontend(p, st));
-        k += 1;
+        k += ref_frontend_launches(p.refine);
         if (a.paf_mat) { CU(launch_upsample_nearest(a.paf, a.layout, a.n, a.h, a.w, EKP_PAF_CH, a.paf_mat, st)); k += 1; }
         if (a.heat_mat) { CU(launch_upsample_nearest(a.heat, a.layout, a.n, a.h, a.w, EKP_HEAT_CH, a.heat_mat, st)); k += 1; }
         src.ptr = a.paf; src.mode = PAF_LO_NEAREST;  // == paf_mat[y][x] exactly (cv2 INTER_NEAREST x8)

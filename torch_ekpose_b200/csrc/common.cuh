@@ -74,6 +74,35 @@ __device__ __forceinline__ float lo_at(const float* lo, int layout, int img, int
                                      : __ldg(lo + (((size_t) img * h + j) * w + i) * C + c);
 }
 
+// ---- TMA bulk load of a contiguous, 16-byte aligned range into shared memory (cp.async.bulk global -> shared, SASS
+// UBLKCP.S.G), completion counted in bytes on an mbarrier: one thread arms the barrier and issues the copy, every
+// thread waits on the barrier's phase.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned) __cvta_generic_to_shared(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned) __cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // One packed result record per image, so a batch's results are a single device-to-host copy:
 //   [0]           int num_humans, int n_peaks, unsigned overflow, int pad
 //   [off_subset]  float  subset[max_humans][20]      rows as the reference keeps them
@@ -120,10 +149,6 @@ struct ConnectParams {
     Conn* conns;               // [n][19][max_part]
     int* n_conns;              // [n][19]
     unsigned* overflow;
-    // fused assembly: the block that finishes an image's last limb runs assemble_image on it (assemble.cuh)
-    int fuse_assemble;
-    int* limb_done;            // [n] finished limb blocks per image; the assembling block resets its counter to 0
-    AsmParams assemble;
 };
 
 struct DenseParams {

@@ -530,6 +530,20 @@ __device__ __forceinline__ void nms_task_at(const DenseParams& p, int img, int c
         const int m = m0 + b;
         window(m);
         if (m >= 2 && m <= h - 3) {  // interior block: taps are immediates from the constant bank
+            // Exact early-out per row block from the lanes' own horizontal results: taps >= 0, so no row of the block
+            // exceeds sum_j max_phase(tap_j) * max(T_j, 0) in this lane's column; if that stays below the threshold in every
+            // lane, none of the 8 rows holds a peak, and as neighbours they cannot outweigh a value above the threshold
+            // either: the pending row is tested against -inf and the block is skipped (same peaks, tests/test_gpu_parity.py).
+            float bound = __fmul_rn(cTapsInteriorMax[0], fmaxf(T0, 0.f));
+            bound = fmaf(cTapsInteriorMax[1], fmaxf(T1, 0.f), bound);
+            bound = fmaf(cTapsInteriorMax[2], fmaxf(T2, 0.f), bound);
+            bound = fmaf(cTapsInteriorMax[3], fmaxf(T3, 0.f), bound);
+            bound = fmaf(cTapsInteriorMax[4], fmaxf(T4, 0.f), bound);
+            if (!kDebug && !__any_sync(0xffffffffu, inb && bound > p.thr * 0.9999f)) {
+                nms_row(st, NEG_INF, X, 8 * m, out_lane, p.thr, c, sink);   // tests row 8m - 1
+                st.hm2 = NEG_INF; st.hm1 = NEG_INF; st.s1 = NEG_INF;        // rows 8m .. 8m + 7: nothing above the threshold
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 float acc = __fmul_rn(cTapsInterior[k][0], T0);
@@ -712,32 +726,6 @@ dense_frontend_kernel(const DenseParams p) {
 // Same arithmetic, same peaks as the tiled kernels (tests/test_gpu_parity.py); 43 M -> ~21 M warp instructions on the
 // 64 x 368x432 batch (the tiled kernel spent ~60 % of its instructions on staging and the early-out tables).
 constexpr int kPlaneThreads = 256;
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned) __cvta_generic_to_shared(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"((unsigned) __cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)),
-        "r"(parity)
-        : "memory");
-}
 
 // A plane may be cut into `slices` groups of row-block pairs (blockIdx.z), each staging only its rows + halo -- still
 // one contiguous range of the plane -- so that a small batch of big maps fills the GPU (16 x 1312x736: 288 -> 864 CTAs).

@@ -24,9 +24,6 @@
 //    then the final insertion sort), which reproduces the reference's permutation exactly.
 #include <stdlib.h>
 
-#include <algorithm>
-
-#include "assemble.cuh"
 #include "common.cuh"
 
 namespace ekp {
@@ -781,27 +778,14 @@ __device__ __forceinline__ void connect_limb(const ConnectParams& P, unsigned ch
 #endif
 }
 
+// One launch per batch: grid (19 limbs, n images).  (Running the assembly in the same launch -- the block that finishes
+// an image's last limb assembles it -- was built and measured in round 2: no gain once a batch is one CUDA graph launch,
+// 98.9 vs 100.7 us on 64 x 368x432 and 211.9 vs 214.0 us on 16 crowded 1312x736, and 3 % slower on 256 x 656x368 because
+// the assembly's shared memory and registers cost the connect blocks occupancy; removed again, profiles/README.md.)
 template <int kSrc, int kT>
 __global__ void __launch_bounds__(kT) paf_connect_kernel(const ConnectParams P) {
     extern __shared__ __align__(16) unsigned char conn_smem[];
     connect_limb<kSrc, kT>(P, conn_smem);
-    if (!P.fuse_assemble) return;
-    // ---- optional (EKP_FUSE_ASSEMBLE=1, off by default: measured no faster, capi.cu) fused second half of stage 5: the
-    // block that completes an image's 19th limb assembles the image right away (no second launch).  Writers: conns /
-    // n_conns / overflow -> barrier -> device-scope fence -> counter; the last block: counter -> fence -> reads.
-    __shared__ int sIsLast;
-    __syncthreads();
-    const int img = blockIdx.y;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int done = atomicAdd(P.limb_done + img, 1);
-        sIsLast = done == EKP_NUM_LIMB - 1;
-        if (sIsLast) P.limb_done[img] = 0;   // ready for the next batch
-    }
-    __syncthreads();
-    if (!sIsLast) return;
-    __threadfence();
-    assemble_image(P.assemble, img, conn_smem);
 }
 
 // ---- host-pointer process_paf: which elements of the caller's paf_mat does stage 4 read? ---------------
@@ -891,13 +875,9 @@ static cudaError_t launch_src(const ConnectParams& P, int n, size_t smem, int th
 }
 
 // per device, once per context: allow the largest dynamic shared memory this context can ask for
-static size_t fused_assemble_bytes(int max_humans, int max_peaks, int max_part) {
-    return assemble_smem_bytes(max_humans, max_peaks, max_part, assemble_conn_cap(max_humans, max_part));
-}
-cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w, int max_humans, int max_peaks) {
+cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w) {
     size_t big = connect_smem_bytes(max_part, max_cand, max_h * max_w);
     if (big > 200 * 1024) big = connect_smem_bytes(max_part, max_cand, 0);
-    big = std::max(big, fused_assemble_bytes(max_humans, max_peaks, max_part));   // the block that assembles an image reuses the buffer
     if (big > kSmemPerSm) return cudaErrorInvalidValue;
     cudaError_t e = cudaSuccess;
 #define EKP_RAISE(S, T) if (e == cudaSuccess) e = raise_dynamic_smem_limit(paf_connect_kernel<S, T>, big)
@@ -915,11 +895,7 @@ cudaError_t launch_paf_connect(const ConnectParams& P_in, int n, cudaStream_t st
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const bool staged = planes_fit(paf, P.max_part, P.max_cand);
-    size_t smem = connect_smem_bytes(P.max_part, P.max_cand, staged ? paf.h * paf.w : 0);
-    if (P.fuse_assemble) {
-        P.assemble.conn_cap = assemble_conn_cap(P.assemble.max_humans, P.assemble.max_part);
-        smem = std::max(smem, fused_assemble_bytes(P.assemble.max_humans, P.assemble.max_peaks, P.assemble.max_part));
-    }
+    const size_t smem = connect_smem_bytes(P.max_part, P.max_cand, staged ? paf.h * paf.w : 0);
     const int blocks = EKP_NUM_LIMB * n;
     int threads = blocks <= 4 * sms ? 2 * kConnThreads : kConnThreads;
     if (staged && smem > 64 * 1024 && blocks <= 4 * sms) {

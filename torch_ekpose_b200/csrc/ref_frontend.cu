@@ -19,116 +19,201 @@ namespace ekp {
 
 constexpr int kRefWarps = 8;
 
-__global__ void __launch_bounds__(kRefWarps * 32) ref_frontend_kernel(const RefParams p) {
-    __shared__ float sPatch[kRefWarps][25];
-    __shared__ float sTmp[kRefWarps][5 * 40];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = p.h, w = p.w;
-    const long long task = (long long) blockIdx.x * kRefWarps + warp;  // (img, part, row)
-    if (task >= (long long) p.n * EKP_NUM_PART * h) return;
-    const int y = (int) (task % h);
-    const int part = (int) ((task / h) % EKP_NUM_PART);
-    const int img = (int) (task / ((long long) h * EKP_NUM_PART));
-
-    for (int xb = 0; xb < w; xb += 32) {
-        const int x = xb + lane;
-        bool is_max = false;
-        if (x < w) {
-            const float v = lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x);
-            is_max = v > p.thr;
-            if (is_max && x > 0) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x - 1) > v);
-            if (is_max && x < w - 1) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x + 1) > v);
-            if (is_max && y > 0) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y - 1, x) > v);
-            if (is_max && y < h - 1) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y + 1, x) > v);
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, is_max);
-        if (!p.refine) {  // bool_refine_center=False: the maxima themselves, at (c + 0.5) * 8 - 0.5 truncated, heat value as score
-            if (is_max) {
-                const int slot = atomicAdd(p.raw_count + img, 1);
-                if (slot < p.raw_cap) {
-                    RawPeak pk;
-                    pk.x = 8 * x + 3;
-                    pk.y = 8 * y + 3;
-                    pk.score = lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x);
-                    pk.part = part;
-                    pk.key = ((unsigned) y << 16) | (unsigned) x;
-                    p.raw[(size_t) img * p.raw_cap + slot] = pk;
-                }
-            }
-            continue;
-        }
-        while (mask) {  // the whole warp refines one peak at a time
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int px = xb + src;
-            const int x_min = max(px - 2, 0), x_max = min(px + 2, w - 1);
-            const int y_min = max(y - 2, 0), y_max = min(y + 2, h - 1);
-            const int ph = y_max - y_min + 1, pw = x_max - x_min + 1;
-            const int W8 = pw * 8, H8 = ph * 8;
-            __syncwarp();
-            if (lane < ph * pw) {
-                const int r = lane / pw, c = lane - r * pw;
-                sPatch[warp][r * 5 + c] = lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y_min + r, x_min + c);
-            }
-            __syncwarp();
-            // horizontal pass (HResizeCubic): tmp[r][dx]
-            for (int idx = lane; idx < ph * W8; idx += 32) {
-                const int r = idx / W8, dx = idx - r * W8;
-                const int q = dx + 4;
-                const int sx = (q >> 3) - 1;
-                const float* a = p.cubic + (q & 7) * 4;
-                const float* S = sPatch[warp] + r * 5;
-                float v = __fmul_rn(S[min(max(sx - 1, 0), pw - 1)], __ldg(a + 0));
-                v = __fadd_rn(v, __fmul_rn(S[min(max(sx, 0), pw - 1)], __ldg(a + 1)));
-                v = __fadd_rn(v, __fmul_rn(S[min(max(sx + 1, 0), pw - 1)], __ldg(a + 2)));
-                v = __fadd_rn(v, __fmul_rn(S[min(max(sx + 2, 0), pw - 1)], __ldg(a + 3)));
-                sTmp[warp][r * 40 + dx] = v;
-            }
-            __syncwarp();
-            // vertical pass (VResizeCubicVec_32f order) fused with the arg-max
-            float best = -INFINITY;
-            int best_idx = 0x7fffffff;
-            for (int idx = lane; idx < H8 * W8; idx += 32) {
-                const int dy = idx / W8, dx = idx - dy * W8;
-                const int q = dy + 4;
-                const int sy = (q >> 3) - 1;
-                const float* b = p.cubic + (q & 7) * 4;
-                const float* T = sTmp[warp] + dx;
-                float v = __fmul_rn(T[min(max(sy + 2, 0), ph - 1) * 40], __ldg(b + 3));
-                v = __fadd_rn(__fmul_rn(T[min(max(sy + 1, 0), ph - 1) * 40], __ldg(b + 2)), v);
-                v = __fadd_rn(__fmul_rn(T[min(max(sy, 0), ph - 1) * 40], __ldg(b + 1)), v);
-                v = __fadd_rn(__fmul_rn(T[min(max(sy - 1, 0), ph - 1) * 40], __ldg(b + 0)), v);
-                if (v > best || best_idx == 0x7fffffff) { best = v; best_idx = idx; }  // first maximum
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-                if (oi != 0x7fffffff && (best_idx == 0x7fffffff || ov > best || (ov == best && oi < best_idx))) {
-                    best = ov; best_idx = oi;
-                }
-            }
-            if (lane == 0) {
-                const int slot = atomicAdd(p.raw_count + img, 1);
-                if (slot < p.raw_cap) {
-                    RawPeak pk;
-                    pk.x = 8 * x_min + (best_idx % W8);
-                    pk.y = 8 * y_min + (best_idx / W8);
-                    pk.score = best;
-                    pk.part = part;
-                    pk.key = ((unsigned) y << 16) | (unsigned) px;
-                    p.raw[(size_t) img * p.raw_cap + slot] = pk;
-                }
-            }
+// ---- find_peaks: one block per (part, image) ----------------------------------------------------------------------------
+// Writes one RawPeak per maximum: with p.refine == 0 already in its final form (NMS(bool_refine_center=False): the
+// maximum itself at (c + 0.5) * 8 - 0.5 truncated, heat value as score), else the stride-8 cell (x, y) for
+// ref_refine_kernel to replace by the refined peak.
+// NCHW (the network's layout): the part's map is one contiguous plane; the TMA engine brings it into shared memory with a
+// single bulk copy (as in dense_plane_kernel) and the threads walk it linearly -- a third of the instructions of
+// per-element global indexing.  Other layouts / planes that do not fit read global memory directly.
+__device__ __forceinline__ void ref_emit(const RefParams& p, int img, int part, int x, int y, float v, bool is_max) {
+    const unsigned mask = __ballot_sync(0xffffffffu, is_max);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(mask) - 1) base = atomicAdd(p.raw_count + img, __popc(mask));   // one atomic per warp and step
+    base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+    if (is_max) {
+        const int slot = base + __popc(mask & ((1u << lane) - 1u));
+        if (slot < p.raw_cap) {
+            RawPeak pk;
+            pk.x = p.refine ? x : 8 * x + 3;
+            pk.y = p.refine ? y : 8 * y + 3;
+            pk.score = v;
+            pk.part = part;
+            pk.key = ((unsigned) y << 16) | (unsigned) x;
+            p.raw[(size_t) img * p.raw_cap + slot] = pk;
         }
     }
 }
 
+template <bool kPlane>
+__global__ void __launch_bounds__(kRefWarps * 32) ref_scan_kernel(const RefParams p) {
+    extern __shared__ __align__(16) float sPlane[];
+    __shared__ __align__(8) unsigned long long sBar;
+    const int h = p.h, w = p.w, hw = h * w;
+    const int part = blockIdx.x, img = blockIdx.y;
+    if (kPlane) {
+        const float* src = p.heat + ((size_t) img * EKP_HEAT_CH + part) * hw;
+        const bool bulk = (hw & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        if (bulk) {
+            if (threadIdx.x == 0) mbar_init(&sBar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&sBar, (unsigned) hw * 4u);
+                bulk_load(sPlane, src, (unsigned) hw * 4u, &sBar);
+            }
+            mbar_wait(&sBar, 0);
+        } else {
+            for (int i = threadIdx.x; i < hw; i += kRefWarps * 32) sPlane[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const int steps = (hw + kRefWarps * 32 - 1) / (kRefWarps * 32);
+        int y = threadIdx.x / w, x = threadIdx.x - y * w;   // (row, column) of element threadIdx.x, advanced without divisions
+        const int dy = (kRefWarps * 32) / w, dx = (kRefWarps * 32) - dy * w;
+        for (int s = 0, i = threadIdx.x; s < steps; s++, i += kRefWarps * 32) {
+            bool is_max = false;
+            float v = 0.f;
+            if (i < hw) {
+                v = sPlane[i];
+                is_max = v > p.thr && !(x > 0 && sPlane[i - 1] > v) && !(x < w - 1 && sPlane[i + 1] > v) &&
+                         !(y > 0 && sPlane[i - w] > v) && !(y < h - 1 && sPlane[i + w] > v);
+            }
+            ref_emit(p, img, part, x, y, v, is_max);
+            x += dx; y += dy;
+            if (x >= w) { x -= w; y++; }
+        }
+    } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int y = warp; y < h; y += kRefWarps)
+            for (int xb = 0; xb < w; xb += 32) {
+                const int x = xb + lane;
+                bool is_max = false;
+                float v = 0.f;
+                if (x < w) {
+                    v = lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x);
+                    is_max = v > p.thr;
+                    if (is_max && x > 0) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x - 1) > v);
+                    if (is_max && x < w - 1) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y, x + 1) > v);
+                    if (is_max && y > 0) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y - 1, x) > v);
+                    if (is_max && y < h - 1) is_max = !(lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y + 1, x) > v);
+                }
+                ref_emit(p, img, part, x, y, v, is_max);
+            }
+    }
+}
+
+// ---- NMS(): bicubic refinement, one warp per peak, all peaks of the batch at once ------------------------------------
+// (Refining inside the scan -- the warp that found a row's maxima refined them one after the other -- left most of the
+// GPU waiting for the few warps whose rows held peaks: 64 x 368x432 62 -> 57 us even with the cheaper inner loop below.)
+__global__ void __launch_bounds__(kRefWarps * 32) ref_refine_kernel(const RefParams p) {
+    __shared__ float sPatch[kRefWarps][25];
+    __shared__ float sTmp[kRefWarps][5 * 40];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = p.h, w = p.w, img = blockIdx.y;
+    const int count = min(p.raw_count[img], p.raw_cap);
+    for (int slot = blockIdx.x * kRefWarps + warp; slot < count; slot += gridDim.x * kRefWarps) {   // (uniform per warp)
+    __syncwarp();
+    RawPeak* out = p.raw + (size_t) img * p.raw_cap + slot;
+    const int px = out->x, y = out->y, part = out->part;
+    const int x_min = max(px - 2, 0), x_max = min(px + 2, w - 1);
+    const int y_min = max(y - 2, 0), y_max = min(y + 2, h - 1);
+    const int ph = y_max - y_min + 1, pw = x_max - x_min + 1;
+    const int W8 = pw * 8, H8 = ph * 8;
+    if (lane < ph * pw) {
+        const int r = lane / pw, c = lane - r * pw;
+        sPatch[warp][r * 5 + c] = lo_at(p.heat, p.layout, img, EKP_HEAT_CH, h, w, part, y_min + r, x_min + c);
+    }
+    __syncwarp();
+    // Lane = output column (two slots: dx = lane and dx = 32 + lane, a patch is at most 40 columns wide), so the
+    // column's source indices and coefficients are per-lane constants and the row's are warp-uniform: no index
+    // arithmetic per output value.
+    // horizontal pass (HResizeCubic): tmp[r][dx]
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++) {
+        const int dx = 32 * sl + lane;
+        if (dx < W8) {
+            const int q = dx + 4;
+            const int sx = (q >> 3) - 1;
+            const float* a = p.cubic + (q & 7) * 4;
+            const float a0 = __ldg(a + 0), a1 = __ldg(a + 1), a2 = __ldg(a + 2), a3 = __ldg(a + 3);
+            const int c0 = min(max(sx - 1, 0), pw - 1), c1 = min(max(sx, 0), pw - 1), c2 = min(max(sx + 1, 0), pw - 1),
+                      c3 = min(max(sx + 2, 0), pw - 1);
+            for (int r = 0; r < ph; r++) {
+                const float* S = sPatch[warp] + r * 5;
+                float v = __fmul_rn(S[c0], a0);
+                v = __fadd_rn(v, __fmul_rn(S[c1], a1));
+                v = __fadd_rn(v, __fmul_rn(S[c2], a2));
+                v = __fadd_rn(v, __fmul_rn(S[c3], a3));
+                sTmp[warp][r * 40 + dx] = v;
+            }
+        }
+    }
+    __syncwarp();
+    // vertical pass (VResizeCubicVec_32f order) fused with the arg-max: first maximum in row-major order
+    float best = -INFINITY;
+    int best_idx = 0x7fffffff;
+    for (int dy = 0; dy < H8; dy++) {
+        const int q = dy + 4;
+        const int sy = (q >> 3) - 1;
+        const float* b = p.cubic + (q & 7) * 4;   // warp-uniform
+        const float b0 = __ldg(b + 0), b1 = __ldg(b + 1), b2 = __ldg(b + 2), b3 = __ldg(b + 3);
+        const float* T3 = sTmp[warp] + min(max(sy + 2, 0), ph - 1) * 40;
+        const float* T2 = sTmp[warp] + min(max(sy + 1, 0), ph - 1) * 40;
+        const float* T1 = sTmp[warp] + min(max(sy, 0), ph - 1) * 40;
+        const float* T0 = sTmp[warp] + min(max(sy - 1, 0), ph - 1) * 40;
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            const int dx = 32 * sl + lane;
+            if (dx < W8) {
+                float v = __fmul_rn(T3[dx], b3);
+                v = __fadd_rn(__fmul_rn(T2[dx], b2), v);
+                v = __fadd_rn(__fmul_rn(T1[dx], b1), v);
+                v = __fadd_rn(__fmul_rn(T0[dx], b0), v);
+                const int idx = dy * W8 + dx;
+                if (v > best || (v == best && idx < best_idx) || best_idx == 0x7fffffff) { best = v; best_idx = idx; }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+        if (oi != 0x7fffffff && (best_idx == 0x7fffffff || ov > best || (ov == best && oi < best_idx))) {
+            best = ov; best_idx = oi;
+        }
+    }
+    if (lane == 0) {
+        out->x = 8 * x_min + (best_idx % W8);
+        out->y = 8 * y_min + (best_idx / W8);
+        out->score = best;
+    }
+    }
+}
+
 cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream) {
-    const long long tasks = (long long) p.n * EKP_NUM_PART * p.h;
-    const unsigned grid = (unsigned) ((tasks + kRefWarps - 1) / kRefWarps);
-    ref_frontend_kernel<<<grid, kRefWarps * 32, 0, stream>>>(p);
+    const size_t plane_bytes = sizeof(float) * (size_t) ((p.h * p.w + 3) & ~3);
+    if (p.layout == EKP_LAYOUT_NCHW && plane_bytes <= 200 * 1024 && p.w <= kRefWarps * 32)
+        ref_scan_kernel<true><<<dim3(EKP_NUM_PART, p.n), kRefWarps * 32, plane_bytes, stream>>>(p);
+    else
+        ref_scan_kernel<false><<<dim3(EKP_NUM_PART, p.n), kRefWarps * 32, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !p.refine) return e;
+    // the peak counts are only known on the device: a fixed number of blocks per image (about four resident blocks per SM
+    // over the batch), whose warps stride over the image's peak list
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_image = (4 * sms + p.n - 1) / p.n;
+    per_image = per_image < 1 ? 1 : (per_image > (p.raw_cap + kRefWarps - 1) / kRefWarps ? (p.raw_cap + kRefWarps - 1) / kRefWarps : per_image);
+    ref_refine_kernel<<<dim3(per_image, p.n), kRefWarps * 32, 0, stream>>>(p);
     return cudaGetLastError();
+}
+int ref_frontend_launches(int refine) { return refine ? 2 : 1; }
+cudaError_t configure_ref_frontend(int max_h, int max_w) {
+    const size_t plane_bytes = sizeof(float) * (size_t) ((max_h * max_w + 3) & ~3);
+    return raise_dynamic_smem_limit(ref_scan_kernel<true>, plane_bytes <= 200 * 1024 ? plane_bytes : 48 * 1024);
 }
 
 // ---- nearest x8 upsample (paf_to_pose.py:356-359), HWC output --------------------------------
