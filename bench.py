@@ -481,24 +481,60 @@ class Runner:
         self.torch.cuda.empty_cache()
 
 
-def roofline_entry(kernel, bound, n, h, w, materialize, kernel_ms, peak, peak_src, consts, sm_mhz=None):
-    """Roofline of the front-end kernel of one configuration.  HBM-bound when it materialises the operator-surface tensors;
-    the lean kernel moves 65x fewer bytes and is bound by instruction issue (warp instructions per launch from the
-    committed ncu capture / elapsed time against 4 issue slots x 148 SMs x the SM clock)."""
+FRONTEND_KERNELS = {("dense", True): ["dense_frontend_kernel<mat>"], ("dense", False): ["dense_plane_kernel"],
+                    ("reference", False): ["ref_scan_kernel", "ref_refine_kernel"]}
+STAGE_BOUNDS = {
+    "peak_sort": ("peaks_sort_kernel", "latency: one short block per 256 peaks (histogram, scatter, rank within the part's bucket)"),
+    "connect": ("paf_connect_kernel", "latency / occupancy: one block per (limb, image) walks stage, score, compact, sort, assign; "
+                                      "gathers from shared-memory planes (crowds) or L2 (ten lanes per pair)"),
+    "assemble": ("assemble_kernel", "latency: the 19 limbs of an image are a serial chain (one warp per image; float sums in limb order)"),
+}
+
+
+def issue_model(ents, kernel_ms, sm_mhz):
+    """achieved warp instructions / s against 148 SMs x 4 issue slots x the SM clock (instruction counts from the committed
+    ncu capture; refused when the kernel source changed since)."""
+    missing = sum(e is None for e in ents)
+    ents = [e for e in ents if e is not None]
+    if not ents:
+        return {"unavailable": "no ncu capture of this kernel / configuration in profiles/kernels.json"}
+    if any(e["stale"] for e in ents):
+        return {"stale": True, "reason": f"{ents[0]['source']} changed since {ents[0].get('capture')} was captured"}
+    inst = sum(e["warp_instructions_per_launch"] for e in ents)
+    out = {"warp_instructions_per_launch": inst, "issue_active_pct_under_ncu": [e["issue_active_pct"] for e in ents],
+           "source": ents[0].get("capture")}
+    if missing:
+        out["note"] = f"{missing} of the stage's kernels has no capture: a lower bound"
+    if sm_mhz and kernel_ms > 0:
+        ipeak = 148 * 4 * sm_mhz * 1e6
+        out.update(achieved_ginst_s=inst / (kernel_ms / 1e3) / 1e9, peak_ginst_s=ipeak / 1e9, frac=inst / (kernel_ms / 1e3) / ipeak)
+    return out
+
+
+def roofline_entry(frontend, n, h, w, materialize, stage_ms, peak, peak_src, consts, sm_mhz=None):
+    """Rooflines of one configuration.  The front-end kernel is HBM-bound when it materialises the operator-surface
+    tensors; without them it moves 65x fewer bytes and is bound by instruction issue.  Stages 4-5 are short latency-bound
+    kernels: their issue fraction says how far from ANY throughput bound they run."""
+    shape = f"{8 * h}x{8 * w}x{n}"
+    mode = f"{frontend}_{'mat' if materialize else 'lean'}"
+    kernels = FRONTEND_KERNELS.get((frontend, materialize)) or FRONTEND_KERNELS[(frontend, False)]
+    kernel_ms = stage_ms["frontend"]
     ab = algo_bytes(h, w, materialize) * n
     achieved = ab / (kernel_ms / 1000.0) / 1e9 if kernel_ms > 0 else None
-    out = {"kernel": kernel, "bound": bound, "algorithmic_bytes_per_launch": ab, "kernel_ms": kernel_ms,
-           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "peak_source": peak_src}
-    if bound != "hbm":
-        out["note"] = "HBM fraction is small by construction (nothing full-resolution is written); see `issue`"
-        ent = consts.get(f"{kernel}|{8 * h}x{8 * w}x{n}")
-        if ent and not ent["stale"] and sm_mhz:
-            ipeak = 148 * 4 * sm_mhz * 1e6
-            ach = ent["warp_instructions_per_launch"] / (kernel_ms / 1000.0)
-            out["issue"] = {"warp_instructions_per_launch": ent["warp_instructions_per_launch"], "achieved_ginst_s": ach / 1e9,
-                            "peak_ginst_s": ipeak / 1e9, "frac": ach / ipeak, "source": ent.get("capture")}
-        elif ent:
-            out["issue"] = {"stale": True, "reason": f"{ent['source']} changed since {ent.get('capture')} was captured"}
+    ents = [consts.get(f"{k}|{shape}|{mode}") for k in kernels]
+    out = {"kernel": " + ".join(kernels), "bound": "hbm" if materialize and frontend == "dense" else "issue",
+           "algorithmic_bytes_per_launch": ab, "kernel_ms": kernel_ms, "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": achieved / peak if achieved else None, "peak_source": peak_src}
+    if out["bound"] == "hbm":
+        e = ents[0]
+        out["traffic"] = e["dram_bytes_per_launch"] if e and not e["stale"] else None
+    else:
+        out["note"] = "HBM fraction is small by construction (nothing full-resolution is written); the bound is instruction issue: see `issue`"
+        out["issue"] = issue_model(ents, kernel_ms, sm_mhz)
+    stages = {}
+    for st, (kname, why) in STAGE_BOUNDS.items():
+        stages[st] = {"kernel": kname, "ms": stage_ms[st], "bound": why, "issue": issue_model([consts.get(f"{kname}|{shape}|{mode}")], stage_ms[st], sm_mhz)}
+    out["stages_4_5"] = stages
     return out
 
 
@@ -641,11 +677,9 @@ def run_ours(args, rank, local_rank, world):
     def measure(run, name, workload, frontend, materialize, batches, check):
         ips, ms_b = run.throughput(frontend, materialize, batches)
         st = run.isolated_stage_ms(frontend, materialize)
-        kern = ("dense_frontend_kernel<mat>" if materialize else "dense_frontend_kernel<lean>") if frontend == "dense" else "ref_frontend_kernel"
         ent = {"workload": workload, "images_per_s_per_gpu": ips, "ms_per_batch_pipelined": ms_b, "stage_ms_isolated": st,
                "stages_4_5_ms_isolated": st["peak_sort"] + st["connect"] + st["assemble"],
-               "roofline": roofline_entry(kern, "hbm" if materialize else "issue", run.n, run.h, run.w, materialize, st["frontend"], peak,
-                                          peak_src, consts, clk.get("sm_mhz"))}
+               "roofline": roofline_entry(frontend, run.n, run.h, run.w, materialize, st, peak, peak_src, consts, clk.get("sm_mhz"))}
         if check and rank == 0:
             ent["oracle_check"] = run.oracle_check(frontend, materialize)
         configs[name] = ent
@@ -747,7 +781,7 @@ def run_ours(args, rank, local_rank, world):
         per_launch_ms = ms / nb
         ab = algo_bytes(H_LO, W_LO) * BATCH
         achieved = ab / (per_launch_ms / 1000.0) / 1e9
-        traffic_ent = consts.get("dense_frontend_kernel<mat>|368x432x64")
+        traffic_ent = consts.get("dense_frontend_kernel<mat>|368x432x64|dense_mat")
         traffic = traffic_ent["dram_bytes_per_launch"] if traffic_ent and not traffic_ent["stale"] else None
         e2e_val = images / (max(e2e_ms, e2e_wall_ms) / 1000.0)
         line = {
