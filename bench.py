@@ -656,17 +656,19 @@ def run_ours(args, rank, local_rank, world):
             for k in range(N_CTX):
                 with torch.cuda.stream(R.streams[k]):
                     hd_dst[k].copy_(pin_t[k], non_blocking=True)
-    h2d_round(2)
-    barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record(stream)
-    R.fork()
+    h2d_round(4)
     reps = 8
-    h2d_round(reps)
-    R.join()
-    c1.record(stream)
-    barrier()
-    h2d_ceiling = pinned[0].nbytes * reps * N_CTX / (c0.elapsed_time(c1) / 1e3) / 1e9
+    h2d_ceiling = 0.0
+    for _ in range(3):   # best of three rounds: a ceiling
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        R.fork()
+        h2d_round(reps)
+        R.join()
+        c1.record(stream)
+        barrier()
+        h2d_ceiling = max(h2d_ceiling, pinned[0].nbytes * reps * N_CTX / (c0.elapsed_time(c1) / 1e3) / 1e9)
     del hd_dst, pin_t
 
     clk = clocks.stop()
@@ -804,7 +806,7 @@ def run_ours(args, rank, local_rank, world):
                     # ceiling of THIS metric is N x the slowest GPU's concurrent H2D rate, not the sum
                     "h2d_ceiling_gbs_equal_work": min(h2d_all) * world,
                     "frac_of_h2d_ceiling": e2e_val * (h2d / BATCH) / 1e9 / (min(h2d_all) * world) if min(h2d_all) > 0 else None,
-                    "h2d_ceiling_how": f"all ranks at once: {N_CTX} streams x 8 copies of one {h2d} B pinned block each (the same copy the e2e path issues per batch)",
+                    "h2d_ceiling_how": f"all ranks at once: {N_CTX} streams x 8 copies of one {h2d} B pinned block each (the same copy the e2e path issues per batch), best of 3 rounds",
                     "api": f"ekp_postprocess_host + ekp_results_humans; one pinned block per batch (heat|paf, ONE H2D copy); {N_CTX} contexts / "
                            f"{N_CTX} streams so the H2D of one batch overlaps the kernels of the previous one; rank pinned to cores {my_cores[:1]}..{my_cores[-1:]}"},
             "gpu_launches": int(launches), "cuda_graph_batches": int(graph_batches), "clocks": clk,

@@ -746,6 +746,45 @@ def test_repeated_batches_replay_as_cuda_graphs(ek):
     p.close()
 
 
+def test_graph_replay_reads_the_buffers_current_content(ek):
+    """A replayed batch must see what the caller's buffers hold NOW: the same pageable NumPy arrays, the same pinned
+    block and the same device tensors are refilled between submissions (a stream of frames through fixed buffers)."""
+    from torch_ekpose_b200 import synthetic
+    scenes = [synthetic.make_batch(4, 46, 54, (p, p + 2), seed=300 + p) for p in (1, 3, 5)]
+    p = ek.PostProcessor(device=0, max_batch=4, max_h=46, max_w=54, max_peaks=1024, max_humans=32)
+    host_h, host_p = np.empty_like(scenes[0][0]), np.empty_like(scenes[0][1])          # pageable host memory
+    pb = ek.PinnedBatch(4, 46, 54)
+    dev_h, dev_p = torch.empty(host_h.shape, device="cuda"), torch.empty(host_p.shape, device="cuda")
+    for rounds in range(2):
+        for heat, paf in scenes:
+            want = None
+            for kind in ("pageable", "pinned", "device"):
+                if kind == "pageable":
+                    host_h[...] = heat; host_p[...] = paf
+                    p.run(host_h, host_p, frontend="reference")
+                elif kind == "pinned":
+                    np.copyto(pb.heat, heat); np.copyto(pb.paf, paf)
+                    p.run(pb.heat, pb.paf, frontend="reference")
+                else:
+                    dev_h.copy_(torch.from_numpy(heat)); dev_p.copy_(torch.from_numpy(paf))
+                    p.run(dev_h, dev_p, frontend="reference")
+                res = p.results()
+                if want is None:
+                    want = res
+                    for i in range(4):
+                        hw, pw = np.ascontiguousarray(heat[i].transpose(1, 2, 0)), np.ascontiguousarray(paf[i].transpose(1, 2, 0))
+                        _, sub = util.oracle_reference(hw, pw)
+                        n = int(res["num_humans"][i])
+                        assert n == len(sub)
+                        assert_bits_equal(res["subset"][i, :n], sub, f"{kind} image {i}")
+                else:
+                    assert np.array_equal(want["num_humans"], res["num_humans"])
+                    assert_bits_equal(want["subset"], res["subset"], kind)
+    assert p.graph_launches() >= 6
+    pb.close()
+    p.close()
+
+
 def test_context_capacities_and_growth(ek):
     """max_part / max_cand are per-context capacities (ekp_create_ex): a crowd overflows a small context (reported,
     never silent) and fits a big one; postprocess_batch grows the capacities that overflowed and retries, within the
