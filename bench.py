@@ -486,7 +486,7 @@ FRONTEND_KERNELS = {("dense", True): ["dense_frontend_kernel<mat>"], ("dense", F
 STAGE_BOUNDS = {
     "peak_sort": ("peaks_sort_kernel", "latency: one short block per 256 peaks (histogram, scatter, rank within the part's bucket)"),
     "connect": ("paf_connect_kernel", "latency / occupancy: one block per (limb, image) walks stage, score, compact, sort, assign; "
-                                      "gathers from shared-memory planes (crowds) or L2 (ten lanes per pair)"),
+                                      "gathers from L2: ten lanes per pair (ordinary scenes) or one thread per pair in two exact passes (crowds)"),
     "assemble": ("assemble_kernel", "latency: the 19 limbs of an image are a serial chain (one warp per image; float sums in limb order)"),
 }
 

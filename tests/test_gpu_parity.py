@@ -335,6 +335,22 @@ def test_config4_crowded_1312x736(pp, frontend):
         assert_bits_equal(res["subset"][0, :len(sub)], sub, "vs compiled reference")
 
 
+@pytest.mark.parametrize("frontend", ["dense", "reference"])
+def test_heavy_crowds_up_to_80_people(ek, frontend):
+    """Stage 4 in its one-thread-per-pair regime (two exact passes over thousands of pairs per limb) and the assembly with
+    60+ rows, on 1312x736 scenes with 34-38 and 80 people, run three times on the same context (graph replays included),
+    against the oracle."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(2, 92, 164, (34, 38), seed=44)
+    h80, p80 = synthetic.make_batch(1, 92, 164, (80, 80), seed=45)
+    big = ek.PostProcessor(device=0, max_batch=3, max_h=92, max_w=164, max_peaks=4096, max_humans=256, max_part=256, max_cand=4096)
+    for _ in range(3):
+        res = _check_batch(big, np.concatenate([heat, h80]), np.concatenate([paf, p80]), frontend, False, range(3))
+        assert int(res["num_humans"][2]) >= 60
+        assert int(res["n_peaks"][2]) >= 900
+    big.close()
+
+
 @pytest.mark.parametrize("materialize", [True, False])
 def test_large_map_2624x1472(ek, materialize):
     """A map four times the area of the largest BASELINE shape (184 x 328 stride-8 cells, 12 column tiles): tile

@@ -36,7 +36,7 @@ cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, int p3, in
                                          int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream);
 cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int max_part, int id_from_key, int n,
                               ekp_peak* line, int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
-cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w);
+cudaError_t configure_connect(int max_part, int max_cand);
 cudaError_t launch_paf_connect(const ConnectParams& P, int n, cudaStream_t stream);
 cudaError_t configure_assemble(int max_humans, int max_peaks, int max_part);
 cudaError_t launch_assemble(AsmParams P, int n, cudaStream_t stream);
@@ -276,7 +276,7 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
         e = set_interior_taps(t8.data() + 16 * 8);
     }
     if (e == cudaSuccess) e = configure_peaks_sort(max_peaks);
-    if (e == cudaSuccess) e = configure_connect(max_part, max_cand, max_h, max_w);
+    if (e == cudaSuccess) e = configure_connect(max_part, max_cand);
     if (e == cudaSuccess) e = configure_assemble(max_humans, max_peaks, max_part);
     if (e != cudaSuccess) { ctx_free(c); return fail(EKP_ERR_CUDA, "context setup: %s", cudaGetErrorString(e)); }
     *out = c;

@@ -144,8 +144,7 @@ struct ConnectParams {
     int max_peaks, max_part, max_cand;
     PafSource paf;
     int h1;
-    int stage_min_pairs;       // a block stages the limb's planes in shared memory when it has at least this many pairs
-    int by_sample_max_pairs;   // ... and scores with ten lanes per pair when it has at most this many (else one thread per pair)
+    int by_sample_max_pairs;   // a block scores with ten lanes per pair when it has at most this many pairs (else one thread per pair)
     Conn* conns;               // [n][19][max_part]
     int* n_conns;              // [n][19]
     unsigned* overflow;

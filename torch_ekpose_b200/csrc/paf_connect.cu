@@ -34,14 +34,15 @@ namespace ekp {
 constexpr int kConnThreads = EKP_CONN_THREADS;
 constexpr int kMaxPartLimit = 1024;  // upper bound of the per-context max_part (bitmaps of used peaks are static)
 
-// where stage 4 reads the PAF from
+// how stage 4 reads the PAF (gathers from global memory / L2)
 enum ConnSrc {
-    SRC_GLOBAL = 0,       // gathers from global memory, one load per channel
-    SRC_GLOBAL_VEC2 = 1,  // channel-last tensor: both channels of a limb with one 8-byte load
-    SRC_SMEM_PLANES = 2   // the limb's two stride-8 planes staged in shared memory (NCHW network output): the gathers,
-                          // which bound this kernel through the L1 tag rate (one tag per lane per divergent load:
-                          // 23.8 M tags = the whole 80 us of the crowded batch, profiles/README.md), become shared-memory reads
+    SRC_GLOBAL = 0,       // one load per channel
+    SRC_GLOBAL_VEC2 = 1   // channel-last tensor: both channels of a limb with one 8-byte load
 };
+// (Staging the limb's two stride-8 planes in shared memory and gathering there was built and measured in round 2 on
+// 16 x 1312x736 with 20 / 35 / 50 / 80 people per image: 36.9 vs 26.6, 65.2 vs 50.8, 120 vs 116, 420 vs 442 us against
+// these gathers -- the planes leave room for one block per SM, which costs more than the gathers' L1 tag rate until the
+// crowd is so heavy that the O(n^2) rank sort dominates either way; removed again, profiles/r2_crowd_planes_vs_gathers.txt.)
 
 struct Sample2 { float x, y; };
 
@@ -61,48 +62,11 @@ __device__ __forceinline__ Sample2 pair_at(const float* q, int ch1, int ch2) {
     return r;
 }
 
-// The limb's two stride-8 planes (channels ch1, ch1 + 1 of an NCHW tensor: adjacent in memory) interleaved
-// as float2 in shared memory, coalesced (16-byte loads when the planes allow it).
-template <int kT>
-__device__ __forceinline__ void stage_planes(float2* __restrict__ sP, const PafSource& s, int img, int ch1) {
-    const int hw = s.h * s.w;
-    const float* p1 = s.ptr + ((size_t) img * s.C + ch1) * hw;
-    const float* p2 = p1 + hw;
-    if ((hw & 3) == 0 && (reinterpret_cast<uintptr_t>(p1) & 15) == 0) {
-        float4* d = reinterpret_cast<float4*>(sP);
-        for (int i = threadIdx.x; i < (hw >> 2); i += kT) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p1) + i), b = __ldg(reinterpret_cast<const float4*>(p2) + i);
-            d[2 * i] = make_float4(a.x, b.x, a.y, b.y);
-            d[2 * i + 1] = make_float4(a.z, b.z, a.w, b.w);
-        }
-    } else {
-        for (int i = threadIdx.x; i < hw; i += kT) sP[i] = make_float2(__ldg(p1 + i), __ldg(p2 + i));
-    }
-}
-
 // `packed` = index of this sample in the pre-gathered list (PAF_PACKED only)
 template <int kSrc>
-__device__ __forceinline__ Sample2 paf_sample(const PafSource& s, const float2* __restrict__ sP, int img, int ly, int lx, int ch1,
-                                              int ch2, long long packed) {
+__device__ __forceinline__ Sample2 paf_sample(const PafSource& s, int img, int ly, int lx, int ch1, int ch2, long long packed) {
     constexpr bool kVec2 = kSrc == SRC_GLOBAL_VEC2;
     Sample2 r;
-    if (kSrc == SRC_SMEM_PLANES) {  // same values, same arithmetic as the global paths below
-        lx = min(max(lx, 0), s.W - 1);
-        ly = min(max(ly, 0), s.H - 1);
-        if (s.mode == PAF_LO_NEAREST) {
-            const float2 v = sP[(ly >> 3) * s.w + (lx >> 3)];
-            r.x = v.x; r.y = v.y;
-        } else {
-            int i0, i1, j0, j1;
-            float tx, ty;
-            bilin_coord(lx, s.w, i0, i1, tx);
-            bilin_coord(ly, s.h, j0, j1, ty);
-            const float2 c00 = sP[j0 * s.w + i0], c01 = sP[j0 * s.w + i1], c10 = sP[j1 * s.w + i0], c11 = sP[j1 * s.w + i1];
-            r.x = lerp1(lerp1(c00.x, c01.x, tx), lerp1(c10.x, c11.x, tx), ty);
-            r.y = lerp1(lerp1(c00.y, c01.y, tx), lerp1(c10.y, c11.y, tx), ty);
-        }
-        return r;
-    }
     if (s.mode == PAF_PACKED) {
         const float2 v = __ldg(reinterpret_cast<const float2*>(s.ptr) + packed);
         r.x = v.x; r.y = v.y;
@@ -146,8 +110,8 @@ __device__ __forceinline__ Sample2 paf_sample(const PafSource& s, const float2* 
 // float operations of score_pair; false when all four are <= 0.05 (then at most 6 of 10 can pass) or the
 // two peaks coincide (:66).
 template <int kSrc>
-__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, const float2* __restrict__ sP,
-                                              int img, int ch1, int ch2, long long packed0) {
+__device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1, int ch2,
+                                              long long packed0) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
     float vx = (float) dxi, vy = (float) dyi;
     const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
@@ -162,7 +126,7 @@ __device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak&
         const int i = 3 + k;
         const int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);
         const int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
-        sv[k] = paf_sample<kSrc>(paf, sP, img, ly, lx, ch1, ch2, packed0 + i);
+        sv[k] = paf_sample<kSrc>(paf, img, ly, lx, ch1, ch2, packed0 + i);
     }
     bool any = false;
 #pragma unroll
@@ -172,8 +136,8 @@ __device__ __forceinline__ bool pair_may_pass(const ekp_peak& a, const ekp_peak&
 
 // pafprocess.cpp:59-94 for one (a, b) pair.  Returns true when the pair becomes a candidate.
 template <int kSrc>
-__device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, const float2* __restrict__ sP,
-                                           int img, int ch1, int ch2, int h1, float& criterion2, long long packed0) {
+__device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b, const PafSource& paf, int img, int ch1, int ch2, int h1,
+                                           float& criterion2, long long packed0) {
     const int dxi = b.x - a.x, dyi = b.y - a.y;
     float vx = (float) dxi, vy = (float) dyi;
     const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
@@ -190,7 +154,7 @@ __device__ __forceinline__ bool score_pair(const ekp_peak& a, const ekp_peak& b,
     }
     Sample2 sv[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kSrc>(paf, sP, img, ly[i], lx[i], ch1, ch2, packed0 + i);  // independent gathers in flight
+    for (int i = 0; i < 10; i++) sv[i] = paf_sample<kSrc>(paf, img, ly[i], lx[i], ch1, ch2, packed0 + i);  // independent gathers in flight
     float scores = 0.0f;
     int criterion1 = 0;
 #pragma unroll
@@ -530,7 +494,7 @@ __device__ __forceinline__ int score_pairs_by_sample(const PafSource& paf, const
                 const float step_x = __fdiv_rn((float) dxi, 10.0f), step_y = __fdiv_rn((float) dyi, 10.0f);
                 const int lx = (int) __dadd_rn((double) __fadd_rn((float) a.x, __fmul_rn((float) i, step_x)), 0.5);  // roundpaf
                 const int ly = (int) __dadd_rn((double) __fadd_rn((float) a.y, __fmul_rn((float) i, step_y)), 0.5);
-                const Sample2 sv = paf_sample<kSrc>(paf, nullptr, img, ly, lx, ch1, ch2, (packed_base + pidx) * 10 + i);
+                const Sample2 sv = paf_sample<kSrc>(paf, img, ly, lx, ch1, ch2, (packed_base + pidx) * 10 + i);
                 s = __fadd_rn(__fmul_rn(vx, sv.x), __fmul_rn(vy, sv.y));
             }
         }
@@ -556,8 +520,7 @@ __device__ __forceinline__ int score_pairs_by_sample(const PafSource& paf, const
 // ---- stage 4 for one (limb, image): score all nA x nB pairs; candidates end up in pair order (a outer, b inner) in
 // sScore / sTag.  Returns the number of candidates (identical in every thread; may exceed max_cand: overflow).
 template <int kSrc, int kT>
-__device__ __forceinline__ int score_all_pairs(const PafSource& paf, const float2* __restrict__ sP, const ekp_peak* __restrict__ sA,
-                                               const ekp_peak* __restrict__ sB, int nA, int nB, int img, int ch1, int ch2, int h1,
+__device__ __forceinline__ int score_all_pairs(const PafSource& paf, const ekp_peak* __restrict__ sA, const ekp_peak* __restrict__ sB, int nA, int nB, int img, int ch1, int ch2, int h1,
                                                long long packed_base, int max_cand, float* __restrict__ sScore,
                                                unsigned* __restrict__ sTag, unsigned* __restrict__ sTag2, int* sWarpCnt) {
     const int npairs = nA * nB;
@@ -577,7 +540,7 @@ __device__ __forceinline__ int score_all_pairs(const PafSource& paf, const float
             bool keep = false;
             if (pidx < win_end) {
                 const int ia = pidx / nB;
-                keep = pair_may_pass<kSrc>(sA[ia], sB[pidx - ia * nB], paf, sP, img, ch1, ch2, (packed_base + pidx) * 10);
+                keep = pair_may_pass<kSrc>(sA[ia], sB[pidx - ia * nB], paf, img, ch1, ch2, (packed_base + pidx) * 10);
             }
             const int pos = ordered_slot<kT>(keep, sWarpCnt, nsurv);
             if (keep) sTag2[pos] = (unsigned) pidx;
@@ -592,7 +555,7 @@ __device__ __forceinline__ int score_all_pairs(const PafSource& paf, const float
                 const int pidx = (int) sTag2[k];
                 ia = pidx / nB;
                 ib = pidx - ia * nB;
-                pass = score_pair<kSrc>(sA[ia], sB[ib], paf, sP, img, ch1, ch2, h1, crit, (packed_base + pidx) * 10);
+                pass = score_pair<kSrc>(sA[ia], sB[ib], paf, img, ch1, ch2, h1, crit, (packed_base + pidx) * 10);
             }
             const int pos = ordered_slot<kT>(pass, sWarpCnt, total);
             if (pass && pos < max_cand) { sScore[pos] = crit; sTag[pos] = ((unsigned) ia << 16) | (unsigned) ib; }
@@ -603,11 +566,10 @@ __device__ __forceinline__ int score_all_pairs(const PafSource& paf, const float
     return total;
 }
 
-// Dynamic shared memory of one block: [float2 planes h*w (SRC_SMEM_PLANES only)] [sA, sB: max_part peaks each]
-// [sScore, sTag, sScore2, sTag2: max_cand words each].  max_part / max_cand are capacities of the context
+// Dynamic shared memory of one block: [sA, sB: max_part peaks each] [sScore, sTag, sScore2, sTag2: max_cand words each].  max_part / max_cand are capacities of the context
 // (ekp_create_ex), reported through EKP_OVF_PART / EKP_OVF_CANDIDATES when a scene exceeds them.
-size_t connect_smem_bytes(int max_part, int max_cand, int plane_elems) {
-    return sizeof(float2) * (size_t) ((plane_elems + 1) & ~1) + 2 * sizeof(ekp_peak) * (size_t) max_part + 4 * sizeof(float) * (size_t) max_cand;
+size_t connect_smem_bytes(int max_part, int max_cand) {
+    return 2 * sizeof(ekp_peak) * (size_t) max_part + 4 * sizeof(float) * (size_t) max_cand;
 }
 
 // one (limb, image): stage 4, sort, greedy assignment; every thread of the block calls it, every thread returns
@@ -615,8 +577,7 @@ template <int kSrc, int kT>
 __device__ __forceinline__ void connect_limb(const ConnectParams& P, unsigned char* conn_smem) {
     const PafSource& paf = P.paf;
     const int max_part = P.max_part, max_cand = P.max_cand;
-    float2* sPlane = reinterpret_cast<float2*>(conn_smem);
-    ekp_peak* sA = reinterpret_cast<ekp_peak*>(sPlane + (kSrc == SRC_SMEM_PLANES ? (paf.h * paf.w + 1) & ~1 : 0));  // 16-byte aligned
+    ekp_peak* sA = reinterpret_cast<ekp_peak*>(conn_smem);
     ekp_peak* sB = sA + max_part;
     float* sScore = reinterpret_cast<float*>(sB + max_part);
     unsigned* sTag = reinterpret_cast<unsigned*>(sScore + max_cand);
@@ -644,10 +605,6 @@ __device__ __forceinline__ void connect_limb(const ConnectParams& P, unsigned ch
     for (int i = threadIdx.x; i < nA; i += kT) sA[i] = L[offA + i];
     for (int i = threadIdx.x; i < nB; i += kT) sB[i] = L[offB + i];
     if (threadIdx.x < kMaxPartLimit / 32) sUsedA[threadIdx.x] = sUsedB[threadIdx.x] = 0u;
-    // Staging the two planes pays when there are many pairs (a crowd); a handful of pairs is scored straight from L2,
-    // ten lanes per pair (block-uniform decisions; same values either way).
-    const bool staged = kSrc == SRC_SMEM_PLANES && nA * nB >= P.stage_min_pairs;
-    if (staged) stage_planes<kT>(sPlane, paf, img, ch1);
     __syncthreads();
 
     // ---- stage 4: score all nA x nB pairs; candidates end up in pair order (a outer, b inner) --------
@@ -661,13 +618,10 @@ __device__ __forceinline__ void connect_limb(const ConnectParams& P, unsigned ch
             return;
         }
     }
-    // The staged and the gathering form are separate instantiations of the scoring loops (a per-sample branch between
-    // them would keep the compiler from putting a pair's ten samples in flight together: 5x slower, measured).
-    constexpr int kGather = kSrc == SRC_SMEM_PLANES ? SRC_GLOBAL : kSrc;
-    int total;
-    if (staged) total = score_all_pairs<SRC_SMEM_PLANES, kT>(paf, sPlane, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sTag2, sWarpCnt);
-    else if (npairs <= P.by_sample_max_pairs) total = score_pairs_by_sample<kGather, kT>(paf, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sWarpCnt);
-    else total = score_all_pairs<kGather, kT>(paf, nullptr, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sTag2, sWarpCnt);
+    // Few pairs (every ordinary scene): ten lanes per pair, one round trip to L2.  Many: one thread per pair, two exact passes.
+    const int total = npairs <= P.by_sample_max_pairs
+                          ? score_pairs_by_sample<kSrc, kT>(paf, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sWarpCnt)
+                          : score_all_pairs<kSrc, kT>(paf, sA, sB, nA, nB, img, ch1, ch2, P.h1, packed_base, max_cand, sScore, sTag, sTag2, sWarpCnt);
     PROF_MARK(2);  // scoring (both passes)
     // ---- sort (pafprocess.cpp:97).  std::sort's result is only algorithm-dependent in how it
     // permutes EQUAL scores, and for n <= 16 it is a plain (stable) insertion sort.  So: rank every
@@ -850,16 +804,10 @@ cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned
 }
 
 // ---- launch ------------------------------------------------------------------------------------------------
-// Source: shared-memory planes when the stride-8 PAF is NCHW (the network's layout; coalesced staging) and the
-// planes fit; otherwise gathers from global memory, 8-byte ones when the tensor is channel-last, even and aligned.
-// Threads: blocks are latency-bound chains; a batch whose 19 x n blocks all fit on the GPU at once (crowded scenes
-// come in small batches) gets more threads per block, bigger batches keep more blocks resident instead; big planes
-// (one or two blocks per SM) get 512.
+// Gathers: 8-byte ones when the tensor is channel-last, even and aligned.  Threads: blocks are latency-bound chains; a
+// batch whose 19 x n blocks all fit on the GPU at once (crowded scenes come in small batches) gets twice the threads per
+// block, bigger batches keep more blocks resident instead.
 constexpr size_t kSmemPerSm = 227 * 1024;
-static bool planes_fit(const PafSource& paf, int max_part, int max_cand) {
-    return (paf.mode == PAF_LO_NEAREST || paf.mode == PAF_LO_BILINEAR) && paf.layout == EKP_LAYOUT_NCHW &&
-           connect_smem_bytes(max_part, max_cand, paf.h * paf.w) <= 200 * 1024;
-}
 
 template <int kSrc, int kT>
 static cudaError_t launch_one(const ConnectParams& P, int n, size_t smem, cudaStream_t stream) {
@@ -868,22 +816,18 @@ static cudaError_t launch_one(const ConnectParams& P, int n, size_t smem, cudaSt
 }
 template <int kSrc>
 static cudaError_t launch_src(const ConnectParams& P, int n, size_t smem, int threads, cudaStream_t stream) {
-    if (threads == 1024) { if (kSrc == SRC_SMEM_PLANES) return launch_one<SRC_SMEM_PLANES, 1024>(P, n, smem, stream); threads = 512; }
-    if (threads == 512) return launch_one<kSrc, 512>(P, n, smem, stream);
     if (threads == 256) return launch_one<kSrc, 256>(P, n, smem, stream);
     return launch_one<kSrc, 128>(P, n, smem, stream);
 }
 
-// per device, once per context: allow the largest dynamic shared memory this context can ask for
-cudaError_t configure_connect(int max_part, int max_cand, int max_h, int max_w) {
-    size_t big = connect_smem_bytes(max_part, max_cand, max_h * max_w);
-    if (big > 200 * 1024) big = connect_smem_bytes(max_part, max_cand, 0);
+// per device, once per context: allow the dynamic shared memory this context's capacities ask for
+cudaError_t configure_connect(int max_part, int max_cand) {
+    const size_t big = connect_smem_bytes(max_part, max_cand);
     if (big > kSmemPerSm) return cudaErrorInvalidValue;
     cudaError_t e = cudaSuccess;
 #define EKP_RAISE(S, T) if (e == cudaSuccess) e = raise_dynamic_smem_limit(paf_connect_kernel<S, T>, big)
-    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256); EKP_RAISE(SRC_GLOBAL, 512);
-    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256); EKP_RAISE(SRC_GLOBAL_VEC2, 512);
-    EKP_RAISE(SRC_SMEM_PLANES, 128); EKP_RAISE(SRC_SMEM_PLANES, 256); EKP_RAISE(SRC_SMEM_PLANES, 512); EKP_RAISE(SRC_SMEM_PLANES, 1024);
+    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256);
+    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256);
 #undef EKP_RAISE
     return e;
 }
@@ -894,21 +838,12 @@ cudaError_t launch_paf_connect(const ConnectParams& P_in, int n, cudaStream_t st
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool staged = planes_fit(paf, P.max_part, P.max_cand);
-    const size_t smem = connect_smem_bytes(P.max_part, P.max_cand, staged ? paf.h * paf.w : 0);
-    const int blocks = EKP_NUM_LIMB * n;
-    int threads = blocks <= 4 * sms ? 2 * kConnThreads : kConnThreads;
-    if (staged && smem > 64 * 1024 && blocks <= 4 * sms) {
-        static const int env_big = getenv("EKP_CONN_BIG_THREADS") ? atoi(getenv("EKP_CONN_BIG_THREADS")) : 512;
-        threads = env_big;   // one block per SM: every thread it has goes to this limb
-    }
-    // per-block regimes (same results in all of them): up to six rounds of ten-lanes-per-pair scoring straight from L2,
-    // beyond that one thread per pair in two exact passes, on planes staged in shared memory where the launch has them
+    const size_t smem = connect_smem_bytes(P.max_part, P.max_cand);
+    const int threads = EKP_NUM_LIMB * n <= 4 * sms ? 2 * kConnThreads : kConnThreads;
+    // per-block regimes (same results in both): up to six rounds of ten-lanes-per-pair scoring, beyond that one thread per
+    // pair in two exact passes
     static const int env_by_sample = getenv("EKP_BY_SAMPLE_MAX_PAIRS") ? atoi(getenv("EKP_BY_SAMPLE_MAX_PAIRS")) : -1;
-    static const int env_stage_min = getenv("EKP_STAGE_MIN_PAIRS") ? atoi(getenv("EKP_STAGE_MIN_PAIRS")) : -1;
     P.by_sample_max_pairs = env_by_sample >= 0 ? env_by_sample : 6 * 3 * (threads / 32);
-    P.stage_min_pairs = env_stage_min >= 0 ? env_stage_min : P.by_sample_max_pairs + 1;
-    if (staged) return launch_src<SRC_SMEM_PLANES>(P, n, smem, threads, stream);
     // both PAF channels of a limb with one 8-byte load: channel-last tensor, even channel count, aligned base
     const bool channel_last = paf.mode != PAF_PACKED && (paf.mode == PAF_FULL_HWC || paf.layout == EKP_LAYOUT_NHWC);
     const bool vec2 = channel_last && paf.C % 2 == 0 && reinterpret_cast<uintptr_t>(paf.ptr) % 8 == 0;
