@@ -51,6 +51,7 @@ H_LO, W_LO = 46, 54     # stride-8 map of a 368x432 image
 PEOPLE = (1, 6)
 INPUT_SETS = 4          # distinct input batches rotated between batches
 N_CTX = int(os.environ.get("EKP_BENCH_CONTEXTS", "4"))   # contexts / CUDA streams the batches rotate over
+N_CTX_CFG = int(os.environ.get("EKP_BENCH_CFG_CONTEXTS", "4"))   # ... in the configs[2] / configs[3] context legs
 
 
 def algo_bytes(h, w, materialize=True):
@@ -679,7 +680,7 @@ def run_ours(args, rank, local_rank, world):
     def measure(run, name, workload, frontend, materialize, batches, check):
         ips, ms_b = run.throughput(frontend, materialize, batches)
         st = run.isolated_stage_ms(frontend, materialize)
-        ent = {"workload": workload, "images_per_s_per_gpu": ips, "ms_per_batch_pipelined": ms_b, "stage_ms_isolated": st,
+        ent = {"workload": workload, "contexts": len(run.pps), "images_per_s_per_gpu": ips, "ms_per_batch_pipelined": ms_b, "stage_ms_isolated": st,
                "stages_4_5_ms_isolated": st["peak_sort"] + st["connect"] + st["assemble"],
                "roofline": roofline_entry(frontend, run.n, run.h, run.w, materialize, st, peak, peak_src, consts, clk.get("sm_mhz"))}
         if check and rank == 0:
@@ -695,7 +696,7 @@ def run_ours(args, rank, local_rank, world):
     if not args.headline_only:
         # configs[2]: 656x368 frames, batch 256
         R3 = Runner(ek, torch, dev, local_rank, 256, 46, 82, (2, 8), seed=300 + 7 * rank, max_peaks=1024, max_humans=32, max_part=64,
-                    max_cand=512, nctx=2, nsets=2)
+                    max_cand=512, nctx=N_CTX_CFG, nsets=2)
         measure(R3, "c3_656x368_x256_dense_materialised", "configs[2]: 656x368, batch 256, dense front-end + operator-surface tensors", "dense", True, 12, True)
         measure(R3, "c3_656x368_x256_dense_lean", "configs[2] without materialisation", "dense", False, 40, False)
         measure(R3, "c3_656x368_x256_reference_lean", "configs[2], reference front-end", "reference", False, 40, True)
@@ -703,7 +704,7 @@ def run_ours(args, rank, local_rank, world):
         R3.close()
         # configs[3]: crowded 1312x736, 30-40 people, batch 16
         R4 = Runner(ek, torch, dev, local_rank, 16, 92, 164, (30, 40), seed=400 + 7 * rank, max_peaks=2048, max_humans=128, max_part=128,
-                    max_cand=1024, nctx=2, nsets=2)
+                    max_cand=1024, nctx=N_CTX_CFG, nsets=2)
         measure(R4, "c4_1312x736_x16_crowded_dense_materialised", "configs[3]: 1312x736, 30-40 people, batch 16, dense front-end + operator-surface tensors", "dense", True, 30, True)
         measure(R4, "c4_1312x736_x16_crowded_dense_lean", "configs[3] without materialisation", "dense", False, 60, True)
         measure(R4, "c4_1312x736_x16_crowded_reference_lean", "configs[3], reference front-end", "reference", False, 60, True)

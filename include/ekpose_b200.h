@@ -52,9 +52,12 @@ typedef enum ekp_layout { EKP_LAYOUT_NCHW = 0, EKP_LAYOUT_NHWC = 1 } ekp_layout;
 typedef enum ekp_frontend {
     EKP_FRONTEND_DENSE = 0,     /* bilinear x8 -> Gaussian sigma 3 -> 3x3 max NMS (BASELINE.json north_star) */
     EKP_FRONTEND_REFERENCE = 1, /* the reference's NMS(): stride-8 cross NMS + bicubic patch refinement */
-    EKP_FRONTEND_REFERENCE_COARSE = 2 /* NMS(bool_refine_center=False) / find_peaks (paf_to_pose.py:26-36, :119-122): the
+    EKP_FRONTEND_REFERENCE_COARSE = 2, /* NMS(bool_refine_center=False) / find_peaks (paf_to_pose.py:26-36, :119-122): the
                                        * stride-8 maxima themselves, reported at (8c + 3) = (int) compute_resized_coords(c, 8)
                                        * (:39-57, truncated like pafprocess.cpp:30-31) with the heat value as score */
+    EKP_FRONTEND_REFERENCE_GAUSS = 3   /* NMS(bool_gaussian_filt=True), paf_to_pose.py:111-112: as REFERENCE, with
+                                       * scipy.ndimage.gaussian_filter(sigma=3) applied to every upsampled patch before the
+                                       * arg-max (no caller in the reference enables it; bit-exact against scipy) */
 } ekp_frontend;
 
 /* per-image overflow bits reported by ekp_results */
@@ -143,6 +146,10 @@ int ekp_results(ekp_ctx *ctx, int *num_humans, float *subset, int *n_peaks, ekp_
  * i.e. get_part_cid / get_part_x / get_part_y / get_part_score in one table, and the human score
  * float32 [n, max_humans] = subset[18] / subset[19] (get_score, pafprocess.cpp:204-206). */
 int ekp_results_humans(ekp_ctx *ctx, int *num_humans, ekp_peak *parts, float *scores, unsigned *overflow);
+
+/* The 13 distinct weights w[-12] .. w[0] of scipy.ndimage's Gaussian kernel for sigma = 3 as the context uploads them for
+ * EKP_FRONTEND_REFERENCE_GAUSS (host-only; tests compare them with scipy's own array). */
+int ekp_scipy_gauss3_weights(double *out13);
 
 /* Test hook: sorts scores (descending, comparator `a.score > b.score`, pafprocess.cpp:244-246) and
  * the tags riding along with the device code's replay of libstdc++'s std::sort, in place, DEVICE

@@ -196,6 +196,10 @@ class Frontend:
         L = self.lib = C.CDLL(PORT_SO)
         L.okp_ref_nms.restype = C.c_int
         L.okp_ref_nms.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _f32p, C.c_int]
+        L.okp_ref_nms_ex.restype = C.c_int
+        L.okp_ref_nms_ex.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _f32p, C.c_int]
+        L.okp_scipy_gauss3.argtypes = [_f32p, C.c_int, C.c_int]
+        L.okp_scipy_gauss3_weights.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
         L.okp_upsample_nearest.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
         L.okp_upsample_bilinear.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p]
         L.okp_resize_cubic.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
@@ -217,13 +221,27 @@ class Frontend:
         assert a.ndim == 3
         return a
 
-    def ref_nms(self, heat, thr=0.15, up=8, nparts=18, cap=8192) -> np.ndarray:
-        """NMS() + joint_list of paf_to_pose_cpp: float32 [N,5] rows (x, y, score, id, part)."""
+    def ref_nms(self, heat, thr=0.15, up=8, nparts=18, cap=8192, gauss=False) -> np.ndarray:
+        """NMS() + joint_list of paf_to_pose_cpp: float32 [N,5] rows (x, y, score, id, part); gauss=True is
+        NMS(bool_gaussian_filt=True), paf_to_pose.py:111-112."""
         heat = self._hwc(heat)
         out = np.zeros((cap, 5), np.float32)
-        n = self.lib.okp_ref_nms(heat, heat.shape[0], heat.shape[1], heat.shape[2], nparts, thr, up, out, cap)
+        n = self.lib.okp_ref_nms_ex(heat, heat.shape[0], heat.shape[1], heat.shape[2], nparts, thr, up, int(bool(gauss)), out, cap)
         assert n <= cap
         return out[:n].copy()
+
+    def scipy_gauss3(self, patch) -> np.ndarray:
+        """scipy.ndimage.gaussian_filter(patch, sigma=3) of a float32 2-D patch (both sides >= 13)."""
+        out = np.ascontiguousarray(patch, np.float32).copy()
+        assert out.ndim == 2 and min(out.shape) > 12
+        self.lib.okp_scipy_gauss3(out, out.shape[0], out.shape[1])
+        return out
+
+    def scipy_gauss3_weights(self) -> np.ndarray:
+        """the 13 distinct weights, w[-12] .. w[0]"""
+        fw = np.zeros(13, np.float64)
+        self.lib.okp_scipy_gauss3_weights(fw)
+        return fw
 
     def resize_cubic(self, patch, up=8) -> np.ndarray:
         patch = np.ascontiguousarray(patch, np.float32)

@@ -165,10 +165,54 @@ def coco_fixture():
     np.savez_compressed(os.path.join(OUT, "coco_append_result.npz"), **d)
 
 
+def border_heat():
+    """18 maps of 46x54 with blobs in the corners, on the edges and one cell away from them (patches of 3x3, 3x5, 4x5 ...
+    cells: the clipped windows of paf_to_pose.py:100-102), plus interior ones."""
+    rng = np.random.default_rng(77)
+    h, w = 46, 54
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    heat = np.zeros((h, w, 19), np.float32)
+    spots = [(0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1), (0, 20), (h - 1, 31), (17, 0), (29, w - 1), (1, 1), (h - 2, w - 2),
+             (1, 40), (22, 1), (10, 10), (30, 25), (20, 44)]
+    for k in range(18):
+        m = np.zeros((h, w))
+        for (cy, cx) in spots:
+            if rng.random() < 0.6:
+                jy, jx = rng.normal(0, 0.35, 2)
+                m = np.maximum(m, rng.uniform(0.5, 1.0) * np.exp(-((yy - cy - jy) ** 2 + (xx - cx - jx) ** 2) / (2 * 0.875 ** 2)))
+        heat[:, :, k] = (m + rng.normal(0, 0.005, (h, w))).astype(np.float32)
+    return heat
+
+
+def nms_gauss_fixture():
+    """NMS(bool_gaussian_filt=True) (paf_to_pose.py:111-112: scipy.ndimage.gaussian_filter(sigma=3) on every upsampled
+    patch before the arg-max) by the reference's own Python on the committed scenes and on a border-stress map, OpenCV's
+    own bicubic code."""
+    p2p, cfg, ref = oracle.reference_python()
+    cv2.ipp.setUseIPP(False)
+    d = {"border_heat": border_heat()}
+    heats = {"border": d["border_heat"]}
+    for name in ("c1_46x54_p3", "c2_46x54_p6", "c3_46x82_p8", "c4_crowd_64x96_p24", "empty_46x54"):
+        with np.load(os.path.join(OUT, name + ".npz")) as z:
+            heats[name] = z["heat"]
+    for name, heat in heats.items():
+        jl = p2p.NMS(heat, upsampFactor=cfg.MODEL.DOWNSAMPLE, bool_gaussian_filt=True, config=cfg)
+        rows = [tuple(pk) + (jt,) for jt, jp in enumerate(jl) for pk in jp]
+        d[name + "_peaks"] = np.array(rows, np.float64).reshape(-1, 5)
+        plain = sum(len(jp) for jp in p2p.NMS(heat, upsampFactor=cfg.MODEL.DOWNSAMPLE, config=cfg))
+        print("nms_gauss", name, "peaks", len(rows), "(without the filter:", plain, ")")
+    cv2.ipp.setUseIPP(True)
+    np.savez_compressed(os.path.join(OUT, "nms_gauss.npz"), **d)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "coco":   # only the f3 fixture (reads the committed scenes)
         oracle.build()
         coco_fixture()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "gauss":  # only the NMS(bool_gaussian_filt=True) fixture (reads the committed scenes)
+        oracle.build()
+        nms_gauss_fixture()
         return
     oracle.build(force=True)
     p2p, cfg, ref = oracle.reference_python()
@@ -185,6 +229,7 @@ def main():
         scene_fixture(name, heat, paf, p2p, cfg, ref, fe)
     kat_fixture(ref)
     coco_fixture()
+    nms_gauss_fixture()
 
 
 if __name__ == "__main__":

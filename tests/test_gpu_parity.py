@@ -178,6 +178,48 @@ def test_nms_dropin(ek):
     assert_bits_equal(flat, g["ref_peaks"], "NMS joint list")
 
 
+@pytest.mark.parametrize("scene", ["border"] + util.SCENES)
+def test_nms_with_gaussian_filter_dropin(ek, scene):
+    """NMS(bool_gaussian_filt=True) (paf_to_pose.py:111-112: scipy's gaussian_filter(sigma=3) on every upsampled patch,
+    double arithmetic, float32 between the two axis passes) against the reference's own Python + SciPy output on the golden
+    scenes and on a map with peaks in the corners, on the edges and next to them (clipped 3x3 ... 4x5-cell windows), and
+    against the oracle: coordinates, ids and float32 scores bit-identical."""
+    g = golden("nms_gauss")
+    heat = g["border_heat"] if scene == "border" else golden(scene)["heat"]
+    lists = ek.NMS(heat, upsampFactor=8, bool_gaussian_filt=True, config=ek.cfg)
+    assert len(lists) == 18 and all(a.dtype == np.float64 and a.shape[1:] == (4,) for a in lists)
+    flat = np.array([tuple(r) + (k,) for k, rows in enumerate(lists) for r in rows], np.float64).reshape(-1, 5)
+    assert_bits_equal(flat, g[scene + "_peaks"], "NMS(bool_gaussian_filt=True) joint list vs the reference's")
+    assert_bits_equal(flat.astype(np.float32), util.frontend().ref_nms(heat, gauss=True), "vs the oracle")
+    # the filter has no effect without refinement (:103-122), as in the reference
+    a = ek.NMS(heat, upsampFactor=8, bool_refine_center=False, bool_gaussian_filt=True, config=ek.cfg)
+    b = ek.NMS(heat, upsampFactor=8, bool_refine_center=False, config=ek.cfg)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_gaussian_refinement_in_a_batch_equals_the_oracle(ek):
+    """frontend='reference_gauss' through the batched entry (NCHW, 8 images, people included): the peak tables and the
+    people are the oracle's for NMS(bool_gaussian_filt=True) peaks."""
+    from torch_ekpose_b200 import synthetic
+    heat, paf = synthetic.make_batch(8, 46, 82, (2, 8), seed=91)
+    p = ek.PostProcessor(device=0, max_batch=8, max_h=46, max_w=82, max_peaks=1024, max_humans=64)
+    import torch
+    p.run(torch.from_numpy(heat).cuda(), torch.from_numpy(paf).cuda(), frontend="reference_gauss")
+    res = p.results(with_peaks=True)
+    fe = util.frontend()
+    for i in range(8):
+        hw = np.ascontiguousarray(heat[i].transpose(1, 2, 0)); pw = np.ascontiguousarray(paf[i].transpose(1, 2, 0))
+        peaks = fe.ref_nms(hw, gauss=True)
+        sub, line = util.oracle_people(peaks, 368, 656, fe.upsample_nearest(pw))
+        n = int(res["num_humans"][i])
+        assert n == len(sub) and int(res["n_peaks"][i]) == len(peaks)
+        assert_bits_equal(res["subset"][i, :n], sub, f"image {i}")
+        rows = res["peaks"][i][:len(peaks)]
+        assert np.array_equal(rows["x"], line[0]) and np.array_equal(rows["y"], line[1])
+        assert_bits_equal(rows["score"], line[2])
+    p.close()
+
+
 def _find_peaks_reference(param, img):
     """The reference's own expression, paf_to_pose.py:34-36 (SciPy is the primitive it imports, :4-6)."""
     from scipy.ndimage import generate_binary_structure, maximum_filter

@@ -154,6 +154,29 @@ def test_dense_definition_on_exact_plateaus_is_arithmetic_defined():
         assert any(ties), f"library-only peak at {(x, y, k)} is not on a plateau"
 
 
+def test_gaussian_restatement_equals_scipy_own_code():
+    """NMS(bool_gaussian_filt=True): okp_scipy_gauss3 == scipy.ndimage.gaussian_filter(sigma=3) bit for bit on float32
+    patches of every size a clipped window gives (3..5 cells x 8), its weights == scipy's own kernel array, and the
+    product library's host-side copy of the weights (what a context uploads) == both."""
+    from scipy.ndimage import gaussian_filter
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    fe = util.frontend()
+    w = _gaussian_kernel1d(3.0, 0, 12)[::-1]
+    assert np.array_equal(w, w[::-1])
+    assert np.array_equal(fe.scipy_gauss3_weights(), w[:13])
+    import ctypes
+    from torch_ekpose_b200 import _lib
+    mine = np.zeros(13, np.float64)
+    assert _lib.lib.ekp_scipy_gauss3_weights(mine.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(mine, w[:13])
+    rng = np.random.default_rng(5)
+    for hh in (24, 32, 40):
+        for ww in (24, 32, 40):
+            for k in range(4):
+                patch = (rng.random((hh, ww)) ** (1 + k)).astype(np.float32) * np.float32(10.0 ** (k - 2))
+                assert_bits_equal(fe.scipy_gauss3(patch), gaussian_filter(patch, sigma=3), f"{hh}x{ww}")
+
+
 @pytest.mark.skipif(not os.path.isdir(oracle.REF_ROOT), reason="/root/reference only exists in the authoring container")
 def test_restatements_equal_reference_python_live():
     cv2 = pytest.importorskip("cv2")
@@ -167,6 +190,9 @@ def test_restatements_equal_reference_python_live():
             jl = p2p.NMS(heat, upsampFactor=8, config=cfg)
             want = np.array([tuple(pk) + (jt,) for jt, jp in enumerate(jl) for pk in jp], np.float32).reshape(-1, 5)
             assert_bits_equal(fe.ref_nms(heat), want, "NMS()")
+            jl = p2p.NMS(heat, upsampFactor=8, bool_gaussian_filt=True, config=cfg)
+            want_g = np.array([tuple(pk) + (jt,) for jt, jp in enumerate(jl) for pk in jp], np.float32).reshape(-1, 5)
+            assert_bits_equal(fe.ref_nms(heat, gauss=True), want_g, "NMS(bool_gaussian_filt=True)")
             humans = p2p.paf_to_pose_cpp(heat, paf, cfg)
             sub, _ = util.oracle_people(want, 8 * h, 8 * w, fe.upsample_nearest(paf))
             assert len(humans) == len(sub)

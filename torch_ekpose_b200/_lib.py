@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("EKPOSE_B200_SO") or os.path.join(HERE, "libekpose_b200
 
 NUM_PART, NUM_LIMB, HEAT_CH, PAF_CH, UP, SUBSET_COLS = 18, 19, 19, 38, 8, 20
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-FRONTEND_DENSE, FRONTEND_REFERENCE, FRONTEND_REFERENCE_COARSE = 0, 1, 2
+FRONTEND_DENSE, FRONTEND_REFERENCE, FRONTEND_REFERENCE_COARSE, FRONTEND_REFERENCE_GAUSS = 0, 1, 2, 3
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
 OVF_PEAKS, OVF_PART, OVF_CANDIDATES, OVF_HUMANS, OVF_BADPEAK = 1, 2, 4, 8, 16
 MAX_PART, MAX_CAND = 256, 2048                                              # EKP_MAX_PART / EKP_MAX_CAND (defaults)
@@ -49,6 +49,7 @@ SIGNATURES = {
     "ekp_process_paf_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "ekp_results": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "ekp_results_humans": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ekp_scipy_gauss3_weights": (_i, [_vp]),
     "ekp_debug_std_sort": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ekp_results_parts": (_i, [_vp, _vp]),
     "ekp_dense_smooth_debug": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

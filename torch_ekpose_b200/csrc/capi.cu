@@ -127,6 +127,26 @@ static void build_cubic_table(float* tab /* [8][4] */) {
     }
 }
 
+// scipy.ndimage's Gaussian kernel for sigma = 3 (radius int(4 * 3 + 0.5) = 12), the 13 distinct weights w[-12] .. w[0]:
+// _gaussian_kernel1d computes exp(-0.5 / sigma^2 * x^2) / sum in double, the sum being numpy's pairwise add.reduce of 25
+// doubles (8 running sums over the first 24, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the 25th).  tests/test_oracle_pinning.py
+// compares oracle/frontend_oracle.c's copy of this with scipy's own array, tests/test_abi.py this one with the oracle's.
+static void build_scipy_gauss3(double* fw /* [13] */) {
+    volatile double phi[25], r[8];
+    for (int j = -12; j <= 12; j++) phi[j + 12] = exp(-0.5 / 9.0 * (double) (j * j));
+    for (int j = 0; j < 8; j++) r[j] = phi[j];
+    for (int i = 8; i < 24; i += 8)
+        for (int j = 0; j < 8; j++) r[j] = r[j] + phi[i + j];
+    volatile double sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    sum = sum + phi[24];
+    for (int j = 0; j < 13; j++) fw[j] = phi[j] / sum;
+}
+extern "C" int ekp_scipy_gauss3_weights(double* out13) {
+    if (!out13) return fail(EKP_ERR_ARG, "ekp_scipy_gauss3_weights: NULL");
+    build_scipy_gauss3(out13);
+    return EKP_OK;
+}
+
 // ---- context -----------------------------------------------------------------------------------
 // arguments of one batch submission (also the key of its CUDA graph)
 struct PostArgs {
@@ -167,6 +187,7 @@ struct ekp_ctx {
     float* ay = nullptr;
     int tab_h = 0, tab_w = 0;
     float* cubic = nullptr;         // [8][4]
+    double* gauss = nullptr;        // [13]
     void* prep_tab = nullptr;       // resize tables of the input side for (prep_sh, prep_sw, prep_dest)
     int prep_sh = 0, prep_sw = 0, prep_dest = 0, prep_rh = 0, prep_rw = 0;
     // pinned host mirrors of the results
@@ -198,7 +219,7 @@ static int ctx_free(ekp_ctx* c) {
     if (!c) return EKP_OK;
     cudaSetDevice(c->device);
     void* dev[] = {c->raw, c->raw_count, c->line, c->part_off, c->n_peaks, c->conns, c->n_conns, c->records,
-                   c->in_block, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic, c->prep_tab};
+                   c->in_block, c->mat_heat, c->mat_paf, c->ax, c->ay, c->cubic, c->gauss, c->prep_tab};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {c->h_records, c->h_line};
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -261,11 +282,15 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     c->lay.stride = (c->lay.off_hscore + sizeof(float) * (size_t) max_humans + 15) & ~(size_t) 15;
     DEV_ALLOC(c->records, c->lay.stride * B);
     DEV_ALLOC(c->cubic, sizeof(float) * 32);
+    DEV_ALLOC(c->gauss, sizeof(double) * 13);
     HOST_ALLOC(c->h_records, c->lay.stride * B);
     HOST_ALLOC(c->h_line, sizeof(ekp_peak) * B * max_peaks);
     float cubic[32];
     build_cubic_table(cubic);
     e = cudaMemcpy(c->cubic, cubic, sizeof(cubic), cudaMemcpyHostToDevice);
+    double gauss[13];
+    build_scipy_gauss3(gauss);
+    if (e == cudaSuccess) e = cudaMemcpy(c->gauss, gauss, sizeof(gauss), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = configure_dense_frontend();
     if (e == cudaSuccess) e = configure_dense_plane(max_h, max_w);
@@ -419,7 +444,8 @@ static int enqueue_batch(ekp_ctx* c, const PostArgs& a, cudaStream_t st, int* ke
         RefParams p;
         p.heat = a.heat; p.n = a.n; p.h = a.h; p.w = a.w; p.layout = a.layout; p.thr = a.thr;
         p.raw = c->raw; p.raw_count = c->raw_count; p.raw_cap = c->max_peaks; p.cubic = c->cubic;
-        p.refine = a.frontend == EKP_FRONTEND_REFERENCE ? 1 : 0;
+        p.gauss = c->gauss;
+        p.refine = a.frontend == EKP_FRONTEND_REFERENCE ? 1 : (a.frontend == EKP_FRONTEND_REFERENCE_GAUSS ? 2 : 0);
         CU(launch_ref_frontend(p, st));
         k += ref_frontend_launches(p.refine);
         if (a.paf_mat) { CU(launch_upsample_nearest(a.paf, a.layout, a.n, a.h, a.w, EKP_PAF_CH, a.paf_mat, st)); k += 1; }
@@ -487,7 +513,8 @@ static int submit_batch(ekp_ctx* c, const PostArgs& a, cudaStream_t st) {
 static int check_post_args(const ekp_ctx* c, int n, int h, int w, int layout, int frontend, const char* who) {
     int rc = check_shape(c, n, h, w, layout, who);
     if (rc) return rc;
-    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE && frontend != EKP_FRONTEND_REFERENCE_COARSE)
+    if (frontend != EKP_FRONTEND_DENSE && frontend != EKP_FRONTEND_REFERENCE && frontend != EKP_FRONTEND_REFERENCE_COARSE &&
+        frontend != EKP_FRONTEND_REFERENCE_GAUSS)
         return fail(EKP_ERR_ARG, "%s: frontend %d", who, frontend);
     return EKP_OK;
 }

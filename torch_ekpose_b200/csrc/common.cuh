@@ -174,7 +174,9 @@ struct RefParams {
     int* raw_count;
     int raw_cap;
     const float* cubic; // [8][4] cv2 bicubic coefficients for t = (2k+1)/16
-    int refine;         // 0: report the stride-8 maxima themselves (NMS(bool_refine_center=False), paf_to_pose.py:119-122)
+    const double* gauss; // [13] scipy gaussian_filter(sigma=3) weights w[-12] .. w[0] (refine == 2)
+    int refine;         // 0: report the stride-8 maxima themselves (NMS(bool_refine_center=False), paf_to_pose.py:119-122);
+                        // 1: bicubic refinement; 2: ... with the Gaussian on the upsampled patch (bool_gaussian_filt, :111-112)
 };
 
 }  // namespace ekp

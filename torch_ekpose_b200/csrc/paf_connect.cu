@@ -816,6 +816,7 @@ static cudaError_t launch_one(const ConnectParams& P, int n, size_t smem, cudaSt
 }
 template <int kSrc>
 static cudaError_t launch_src(const ConnectParams& P, int n, size_t smem, int threads, cudaStream_t stream) {
+    if (threads == 512) return launch_one<kSrc, 512>(P, n, smem, stream);
     if (threads == 256) return launch_one<kSrc, 256>(P, n, smem, stream);
     return launch_one<kSrc, 128>(P, n, smem, stream);
 }
@@ -826,8 +827,8 @@ cudaError_t configure_connect(int max_part, int max_cand) {
     if (big > kSmemPerSm) return cudaErrorInvalidValue;
     cudaError_t e = cudaSuccess;
 #define EKP_RAISE(S, T) if (e == cudaSuccess) e = raise_dynamic_smem_limit(paf_connect_kernel<S, T>, big)
-    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256);
-    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256);
+    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256); EKP_RAISE(SRC_GLOBAL, 512);
+    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256); EKP_RAISE(SRC_GLOBAL_VEC2, 512);
 #undef EKP_RAISE
     return e;
 }
@@ -839,7 +840,8 @@ cudaError_t launch_paf_connect(const ConnectParams& P_in, int n, cudaStream_t st
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = connect_smem_bytes(P.max_part, P.max_cand);
-    const int threads = EKP_NUM_LIMB * n <= 4 * sms ? 2 * kConnThreads : kConnThreads;
+    static const int env_crowd_threads = getenv("EKP_CONN_CROWD_THREADS") ? atoi(getenv("EKP_CONN_CROWD_THREADS")) : 2 * kConnThreads;
+    const int threads = EKP_NUM_LIMB * n <= 4 * sms ? env_crowd_threads : kConnThreads;
     // per-block regimes (same results in both): up to six rounds of ten-lanes-per-pair scoring, beyond that one thread per
     // pair in two exact passes
     static const int env_by_sample = getenv("EKP_BY_SAMPLE_MAX_PAIRS") ? atoi(getenv("EKP_BY_SAMPLE_MAX_PAIRS")) : -1;

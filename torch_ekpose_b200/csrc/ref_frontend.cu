@@ -5,6 +5,7 @@
 //   find_peaks :26-36   stride-8 NMS with the 4-neighbour cross footprint (scipy maximum_filter,
 //                       mode='reflect' == in-bounds neighbours only), value > THRESH_HEATMAP;
 //   NMS :60-133         per peak: clip a (<=5)x(<=5) window, cv2.resize(fx=8, fy=8, INTER_CUBIC),
+//                       [bool_gaussian_filt: scipy.ndimage.gaussian_filter(sigma=3) of that patch, :111-112,]
 //                       first arg-max -> refined integer full-resolution coordinate and score;
 //   paf_to_pose_cpp :356-359  cv2.resize(INTER_NEAREST) x8 of PAF / heat (upsample_nearest_kernel,
 //                       only when the caller asks for the operator-surface tensors).
@@ -107,10 +108,21 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_scan_kernel(const RefParam
 // ---- NMS(): bicubic refinement, one warp per peak, all peaks of the batch at once ------------------------------------
 // (Refining inside the scan -- the warp that found a row's maxima refined them one after the other -- left most of the
 // GPU waiting for the few warps whose rows held peaks: 64 x 368x432 62 -> 57 us even with the cheaper inner loop below.)
+// kGauss: NMS(bool_gaussian_filt=True).  The upsampled patch goes through scipy.ndimage.gaussian_filter(sigma=3) before
+// the arg-max: radius 12, one correlate1d per axis (axis 0 first, float32 in between), 'reflect' extension, and because
+// the kernel is symmetric NI_Correlate1D evaluates  tmp = x[i] w[0];  tmp += (x[i+jj] + x[i-jj]) w[jj], jj = -12 .. -1
+// in double -- the same operations here (oracle/frontend_oracle.c okp_scipy_gauss3, pinned bit-for-bit to scipy).
+constexpr int kGaussPatch = 40 * 40;   // floats per buffer; two buffers per warp (dynamic shared memory)
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - 1 - i : i); }  // radius 12 < n
+
+template <bool kGauss>
 __global__ void __launch_bounds__(kRefWarps * 32) ref_refine_kernel(const RefParams p) {
+    extern __shared__ __align__(16) float sGaussBuf[];   // kGauss: [kRefWarps][2][kGaussPatch]
     __shared__ float sPatch[kRefWarps][25];
     __shared__ float sTmp[kRefWarps][5 * 40];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sV = sGaussBuf + (size_t) warp * 2 * kGaussPatch;   // the upsampled patch, row stride 40
+    float* sT = sV + kGaussPatch;                              // ... after the axis-0 pass
     const int h = p.h, w = p.w, img = blockIdx.y;
     const int count = min(p.raw_count[img], p.raw_cap);
     for (int slot = blockIdx.x * kRefWarps + warp; slot < count; slot += gridDim.x * kRefWarps) {   // (uniform per warp)
@@ -171,8 +183,49 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_refine_kernel(const RefPar
                 v = __fadd_rn(__fmul_rn(T2[dx], b2), v);
                 v = __fadd_rn(__fmul_rn(T1[dx], b1), v);
                 v = __fadd_rn(__fmul_rn(T0[dx], b0), v);
+                if (kGauss) { sV[dy * 40 + dx] = v; continue; }
                 const int idx = dy * W8 + dx;
                 if (v > best || (v == best && idx < best_idx) || best_idx == 0x7fffffff) { best = v; best_idx = idx; }
+            }
+        }
+    }
+    if (kGauss) {
+        double fw[13];
+#pragma unroll
+        for (int j = 0; j < 13; j++) fw[j] = __ldg(p.gauss + j);   // fw[12 + jj] = w[jj]
+        __syncwarp();
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {   // axis 0 (along y): lane = column
+            const int dx = 32 * sl + lane;
+            if (dx < W8) {
+                for (int dy = 0; dy < H8; dy++) {
+                    double tmp = __dmul_rn((double) sV[dy * 40 + dx], fw[12]);
+#pragma unroll
+                    for (int jj = -12; jj < 0; jj++) {
+                        const double a = (double) sV[reflect1(dy + jj, H8) * 40 + dx], b = (double) sV[reflect1(dy - jj, H8) * 40 + dx];
+                        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(a, b), fw[12 + jj]));
+                    }
+                    sT[dy * 40 + dx] = __double2float_rn(tmp);
+                }
+            }
+        }
+        __syncwarp();
+        for (int dy = 0; dy < H8; dy++) {   // axis 1 (along x) fused with the arg-max
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int dx = 32 * sl + lane;
+                if (dx < W8) {
+                    const float* T = sT + dy * 40;
+                    double tmp = __dmul_rn((double) T[dx], fw[12]);
+#pragma unroll
+                    for (int jj = -12; jj < 0; jj++) {
+                        const double a = (double) T[reflect1(dx + jj, W8)], b = (double) T[reflect1(dx - jj, W8)];
+                        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(a, b), fw[12 + jj]));
+                    }
+                    const float v = __double2float_rn(tmp);
+                    const int idx = dy * W8 + dx;
+                    if (v > best || (v == best && idx < best_idx) || best_idx == 0x7fffffff) { best = v; best_idx = idx; }
+                }
             }
         }
     }
@@ -192,6 +245,7 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_refine_kernel(const RefPar
     }
 }
 
+constexpr size_t kGaussBytes = sizeof(float) * 2 * kGaussPatch * kRefWarps;
 cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream) {
     const size_t plane_bytes = sizeof(float) * (size_t) ((p.h * p.w + 3) & ~3);
     if (p.layout == EKP_LAYOUT_NCHW && plane_bytes <= 200 * 1024 && p.w <= kRefWarps * 32)
@@ -207,13 +261,16 @@ cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int per_image = (4 * sms + p.n - 1) / p.n;
     per_image = per_image < 1 ? 1 : (per_image > (p.raw_cap + kRefWarps - 1) / kRefWarps ? (p.raw_cap + kRefWarps - 1) / kRefWarps : per_image);
-    ref_refine_kernel<<<dim3(per_image, p.n), kRefWarps * 32, 0, stream>>>(p);
+    if (p.refine == 2) ref_refine_kernel<true><<<dim3(per_image, p.n), kRefWarps * 32, kGaussBytes, stream>>>(p);
+    else ref_refine_kernel<false><<<dim3(per_image, p.n), kRefWarps * 32, 0, stream>>>(p);
     return cudaGetLastError();
 }
 int ref_frontend_launches(int refine) { return refine ? 2 : 1; }
 cudaError_t configure_ref_frontend(int max_h, int max_w) {
     const size_t plane_bytes = sizeof(float) * (size_t) ((max_h * max_w + 3) & ~3);
-    return raise_dynamic_smem_limit(ref_scan_kernel<true>, plane_bytes <= 200 * 1024 ? plane_bytes : 48 * 1024);
+    cudaError_t e = raise_dynamic_smem_limit(ref_scan_kernel<true>, plane_bytes <= 200 * 1024 ? plane_bytes : 48 * 1024);
+    if (e == cudaSuccess) e = raise_dynamic_smem_limit(ref_refine_kernel<true>, kGaussBytes);
+    return e;
 }
 
 // ---- nearest x8 upsample (paf_to_pose.py:356-359), HWC output --------------------------------

@@ -34,7 +34,7 @@ except Exception:  # pragma: no cover
 
 _PEAK_DT = np.dtype([("x", np.int32), ("y", np.int32), ("score", np.float32), ("id", np.int32)])
 _FRONTENDS = {"dense": _lib.FRONTEND_DENSE, "reference": _lib.FRONTEND_REFERENCE,
-              "reference_coarse": _lib.FRONTEND_REFERENCE_COARSE}
+              "reference_coarse": _lib.FRONTEND_REFERENCE_COARSE, "reference_gauss": _lib.FRONTEND_REFERENCE_GAUSS}
 _LAYOUTS = {"nchw": _lib.LAYOUT_NCHW, "nhwc": _lib.LAYOUT_NHWC}
 
 
@@ -108,9 +108,10 @@ class PostProcessor:
         """Submit one batch (n <= max_batch).  CUDA tensors take the device entry point; NumPy
         arrays / CPU tensors take the host entry point (H2D copies on the same stream).
         frontend: 'reference' (default: the reference's own stride-8 NMS + bicubic refinement, i.e. the people
-        paf_to_pose_cpp returns), 'dense' (the north_star formulation) or 'reference_coarse'."""
+        paf_to_pose_cpp returns), 'dense' (the north_star formulation), 'reference_coarse' (NMS(bool_refine_center=False))
+        or 'reference_gauss' (NMS(bool_gaussian_filt=True))."""
         if frontend not in _FRONTENDS:
-            raise ValueError("frontend must be 'dense', 'reference' or 'reference_coarse'")
+            raise ValueError("frontend must be 'dense', 'reference', 'reference_coarse' or 'reference_gauss'")
         n, h, w = self._dims(heat.shape, paf.shape, layout)
         st = self._stream(stream)
         thr = float(np.float32(thr))
@@ -447,11 +448,11 @@ def find_peaks(param, img, device: Optional[int] = None):
 def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False, config=None, device: Optional[int] = None):
     """Drop-in for paf_to_pose.py:60-133: list of 18 float64 arrays ``[n_k, 4]`` = (x, y, score, id).
     bool_refine_center=False returns the stride-8 maxima at compute_resized_coords(peak, 8) with the heat value
-    as score (:119-122)."""
+    as score (:119-122); bool_gaussian_filt=True smooths every upsampled patch with scipy's gaussian_filter(sigma=3)
+    arithmetic before the arg-max (:111-112; it has no effect without refinement, as in the reference)."""
     config = config or default_cfg
-    if bool_gaussian_filt or int(upsampFactor) != 8:
-        raise NotImplementedError("built: upsampFactor=8 (lib/config/default.py:17), bool_gaussian_filt=False (dead code "
-                                  "in the reference, paf_to_pose.py:111-112)")
+    if int(upsampFactor) != 8 or float(upsampFactor) != 8.0:
+        raise NotImplementedError("built: upsampFactor=8 (lib/config/default.py:17 MODEL.DOWNSAMPLE, the only value a caller passes)")
     heatmaps = np.ascontiguousarray(heatmaps, np.float32)
     h, w, _ = heatmaps.shape
     if not bool_refine_center:
@@ -465,7 +466,7 @@ def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=F
             arr[:, 2], arr[:, 3] = rows["score"], rows["id"]
             out.append(arr)
         return out
-    line, po = _peak_table(heatmaps, config.TEST.THRESH_HEATMAP, "reference", device)
+    line, po = _peak_table(heatmaps, config.TEST.THRESH_HEATMAP, "reference_gauss" if bool_gaussian_filt else "reference", device)
     out = []
     for k in range(config.MODEL.NUM_KEYPOINTS):
         rows = line[po[k]:po[k + 1]]
