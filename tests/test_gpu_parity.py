@@ -90,6 +90,33 @@ def test_process_paf_golden(ek, scene, upload, monkeypatch):
         assert np.float32(ek.pafprocess.get_part_score(cid)).view(np.uint32) == g["ref_line_score"][cid].view(np.uint32)
 
 
+def test_process_paf_stream_of_frames(ek):
+    """A video stream through the operator surface: frames with 1-7 people at two shapes, one after the other in one process.
+    Small scenes are replayed as one CUDA graph launch per call (fixed block layout, the peak count travels in the block; a
+    graph per shape and sample size class), bigger ones take the eager path: every frame's people, scores and the
+    part-sorted table behind the getters are the oracle's."""
+    from torch_ekpose_b200 import synthetic
+    fe = util.frontend()
+    frames = [(46, 54, p, 700 + i) for i, p in enumerate([1, 3, 2, 6, 1, 7, 4, 2])] + [(46, 82, p, 720 + i) for i, p in enumerate([2, 5, 3])] + \
+             [(46, 54, p, 740 + i) for i, p in enumerate([3, 0, 5])]
+    for (h, w, people, seed) in frames:
+        heat, paf = synthetic.make_scene(h, w, people, seed)
+        peaks = fe.ref_nms(heat)
+        paf_up = fe.upsample_nearest(paf)
+        if len(peaks) == 0:
+            continue
+        sub, line = util.oracle_people(peaks, 8 * h, 8 * w, paf_up)
+        assert ek.pafprocess.process_paf(peaks[None], np.zeros((8 * h, 8 * w, 19), np.float32), paf_up) == 0
+        n, cids, scores = _compat_subset(ek)
+        assert n == len(sub), (h, w, people)
+        assert np.array_equal(cids, sub[:, :18].astype(np.int32))
+        if n:
+            assert_bits_equal(scores, (sub[:, 18] / sub[:, 19]).astype(np.float32), "human score")
+        for cid in range(0, len(peaks), 7):
+            assert ek.pafprocess.get_part_x(cid) == int(line[0][cid]) and ek.pafprocess.get_part_y(cid) == int(line[1][cid])
+            assert np.float32(ek.pafprocess.get_part_score(cid)).view(np.uint32) == np.float32(line[2][cid]).view(np.uint32)
+
+
 def test_process_paf_pools_all_p1_images(ek):
     """peaks[p1, p2, p3]: the reference walks every (p1, p2) row into ONE peak list (pafprocess.cpp:26-36)."""
     g = golden("c2_46x54_p6")

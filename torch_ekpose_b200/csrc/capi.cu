@@ -11,6 +11,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -32,8 +33,8 @@ cudaError_t launch_peaks_ingest(const float* peaks, const int* n_peaks, int n_fi
                                 int H, RawPeak* raw, int* raw_count, int raw_cap, unsigned* overflow, cudaStream_t stream);
 cudaError_t configure_peaks_sort(int raw_cap);
 int peaks_one_max();
-cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, int p3, int W, int H, int raw_cap, int max_part, ekp_peak* line,
-                                         int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream);
+cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, const int* npk_dev, int p3, int W, int H, int raw_cap, int max_part,
+                                         ekp_peak* line, int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream);
 cudaError_t launch_peaks_sort(const RawPeak* raw, const int* raw_count, int raw_cap, int max_part, int id_from_key, int n,
                               ekp_peak* line, int* part_off, int* n_peaks, unsigned* overflow, cudaStream_t stream);
 cudaError_t configure_connect(int max_part, int max_cand);
@@ -188,10 +189,12 @@ struct ekp_ctx {
     int tab_h = 0, tab_w = 0;
     float* cubic = nullptr;         // [8][4]
     double* gauss = nullptr;        // [13]
+    unsigned long long serial = 0;  // unique per created context (graphs cached outside the context name it)
     void* prep_tab = nullptr;       // resize tables of the input side for (prep_sh, prep_sw, prep_dest)
     int prep_sh = 0, prep_sw = 0, prep_dest = 0, prep_rh = 0, prep_rw = 0;
     // pinned host mirrors of the results
     unsigned char* h_records = nullptr;
+    unsigned char* h_records_dev = nullptr;   // the device's view of the pinned h_records (zero-copy result write-out)
     ekp_peak* h_line = nullptr;
     cudaEvent_t done = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -257,6 +260,8 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     c->device = device; c->max_batch = max_batch; c->max_h = max_h; c->max_w = max_w;
     c->max_peaks = max_peaks; c->max_humans = max_humans; c->max_part = max_part; c->max_cand = max_cand;
     c->graphs = new std::vector<GraphEntry>();
+    static std::atomic<unsigned long long> next_serial{1};
+    c->serial = next_serial++;
     const size_t B = (size_t) max_batch;
 #define DEV_ALLOC(ptr, bytes)                                                     \
     do {                                                                          \
@@ -285,6 +290,7 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     DEV_ALLOC(c->gauss, sizeof(double) * 13);
     HOST_ALLOC(c->h_records, c->lay.stride * B);
     HOST_ALLOC(c->h_line, sizeof(ekp_peak) * B * max_peaks);
+    if (cudaHostGetDevicePointer((void**) &c->h_records_dev, c->h_records, 0) != cudaSuccess) { cudaGetLastError(); c->h_records_dev = nullptr; }
     float cubic[32];
     build_cubic_table(cubic);
     e = cudaMemcpy(c->cubic, cubic, sizeof(cubic), cudaMemcpyHostToDevice);
@@ -375,12 +381,13 @@ static int run_peak_sort(ekp_ctx* c, int n, int id_from_key, cudaStream_t st) {
     c->launches += 1;
     return EKP_OK;
 }
-static int run_connect_assemble(ekp_ctx* c, int n, const PafSource& paf, int h1, cudaStream_t st) {
+// records_direct: device-visible pinned host memory the assembly writes the result records to itself (no D2H copy node)
+static int run_connect_assemble(ekp_ctx* c, int n, const PafSource& paf, int h1, cudaStream_t st, unsigned char* records_direct = nullptr) {
     mark(c, 2, st);
     AsmParams ap;
     ap.line = c->line; ap.max_peaks = c->max_peaks; ap.n_peaks = c->n_peaks; ap.part_off = c->part_off; ap.conns = c->conns;
     ap.n_conns = c->n_conns; ap.max_part = c->max_part; ap.max_humans = c->max_humans; ap.conn_cap = 0; ap.overflow = c->overflow;
-    ap.records = c->records; ap.lay = c->lay;
+    ap.records = records_direct ? records_direct : c->records; ap.lay = c->lay;
     ConnectParams cp;
     cp.line = c->line; cp.part_off = c->part_off; cp.max_peaks = c->max_peaks; cp.max_part = c->max_part; cp.max_cand = c->max_cand;
     cp.paf = paf; cp.h1 = h1; cp.conns = c->conns; cp.n_conns = c->n_conns; cp.overflow = c->overflow;
@@ -390,7 +397,7 @@ static int run_connect_assemble(ekp_ctx* c, int n, const PafSource& paf, int h1,
     mark(c, 4, st);
     if (c->timing) c->timed_runs++;
     c->launches += 2;
-    CU(cudaMemcpyAsync(c->h_records, c->records, c->lay.stride * (size_t) n, cudaMemcpyDeviceToHost, st));  // one packed copy
+    if (!records_direct) CU(cudaMemcpyAsync(c->h_records, c->records, c->lay.stride * (size_t) n, cudaMemcpyDeviceToHost, st));  // one packed copy
     return EKP_OK;
 }
 // after a batch has been put on `st` (eagerly or as a graph launch): results become readable when `done` fires
@@ -848,6 +855,17 @@ int compat_ctx(int need_peaks, int need_humans, int need_part, int need_cand) {
 namespace {
 const long long kListedMaxSamples = 64 * 1024;
 unsigned char* g_listed_host = nullptr; unsigned char* g_listed_dev = nullptr; size_t g_listed_cap = 0;
+enum { TINY_OFF = 0, TINY_ZC = 1, TINY_ZC_GRAPH = 2 };
+unsigned char* g_listed_host_dev = nullptr;   // the device's view of g_listed_host
+struct TinyGraph { unsigned long long ctx_serial; int p3, f1, f2, f3, h1; size_t bytes; cudaGraphExec_t exec; };
+std::vector<TinyGraph> g_tiny;   // under g_mu like everything of the operator surface
+bool g_tiny_ok = true;
+const int kTinyPeaks = 512;
+const long long kTinyMaxSamples = 16384;
+void tiny_graphs_clear() {
+    for (TinyGraph& e : g_tiny) cudaGraphExecDestroy(e.exec);
+    g_tiny.clear();
+}
 const int kHostPairs[EKP_NUM_LIMB][2] = {{1, 2}, {1, 5}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {1, 8}, {8, 9}, {9, 10}, {1, 11},
                                          {11, 12}, {12, 13}, {1, 0}, {0, 14}, {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17}};
 const int kHostPairsNet[EKP_NUM_LIMB] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 28, 30, 34, 32, 36, 18, 26};  // x channel; y = x + 1
@@ -883,15 +901,40 @@ int process_paf_listed(ekp_ctx* c, long long npk, int p3, const float* peaks, in
     pair_base[EKP_NUM_LIMB] = (int) acc;
     const long long nsamples = acc * 10;
     if (nsamples > kListedMaxSamples) return 1;
-    const size_t off_peaks = sizeof(pair_base), off_samp = (off_peaks + sizeof(float) * (size_t) npk * p3 + 7) & ~(size_t) 7;
-    const size_t bytes = off_samp + sizeof(float2) * (size_t) (nsamples > 0 ? nsamples : 1);
+    // Tiny scenes (a handful of people: every frame of an ordinary video).  Such a call used to wait ~25 us for the device-side
+    // chain H2D copy -> 3 kernels -> D2H copy -> event after spending ~25 us submitting it (70 us at 3 people).  Here the
+    // kernels read the pinned block and write the result record THROUGH PCIe themselves (zero-copy: a few KB, one round trip
+    // per kernel), so the chain is the three kernels; and the block has a fixed layout (room for kTinyPeaks peaks, samples
+    // rounded up to a size class, the peak count inside), so the launch arguments depend only on (shape, size class) and the
+    // three launches are replayed as ONE CUDA graph launch (1.5 us to submit).  Measured, raw call at 3 / 8 people: 70 / 112 us
+    // before, 58 / 111 us zero-copy with eager launches, 51 / 103 us as a graph (the copies inside a graph instead: 66 / 116 us;
+    // profiles/README.md).  What is left is the latency of the three kernels themselves (~35 us).
+    // EKP_PROCESS_PAF_TINY = zerocopy_graph (default) | zerocopy (eager launches; also under EKP_GRAPHS=0) | off.
+    static const int tiny_mode = [] {
+        const char* e = getenv("EKP_PROCESS_PAF_TINY");
+        const bool graphs_off = getenv("EKP_GRAPHS") && atoi(getenv("EKP_GRAPHS")) == 0;
+        int m = TINY_ZC_GRAPH;
+        if (e) m = !strcmp(e, "zerocopy_graph") ? TINY_ZC_GRAPH : (!strcmp(e, "zerocopy") ? TINY_ZC : TINY_OFF);
+        if (graphs_off && m == TINY_ZC_GRAPH) m = TINY_ZC;
+        return m;
+    }();
+    const bool tiny = tiny_mode != TINY_OFF && g_tiny_ok && !c->timing && c->h_records_dev && npk <= kTinyPeaks && npk <= peaks_one_max() &&
+                      nsamples <= kTinyMaxSamples;
+    long long samp_class = 2048;
+    while (samp_class < nsamples) samp_class *= 2;
+    pair_base[31] = (int) npk;
+    const size_t off_peaks = sizeof(pair_base);
+    const size_t off_samp = (off_peaks + sizeof(float) * (size_t) (tiny ? kTinyPeaks : npk) * p3 + 7) & ~(size_t) 7;
+    const size_t bytes = off_samp + sizeof(float2) * (size_t) (tiny ? samp_class : (nsamples > 0 ? nsamples : 1));
     if (g_listed_cap < bytes) {
+        tiny_graphs_clear();   // they copy from / to the old blocks
         if (g_listed_host) cudaFreeHost(g_listed_host);
         if (g_listed_dev) cudaFree(g_listed_dev);
         g_listed_host = nullptr; g_listed_dev = nullptr; g_listed_cap = 0;
         const size_t cap = bytes + bytes / 2 + 4096;
         CU(cudaMallocHost((void**) &g_listed_host, cap));
         CU(cudaMalloc((void**) &g_listed_dev, cap));
+        CU(cudaHostGetDevicePointer((void**) &g_listed_host_dev, g_listed_host, 0));
         g_listed_cap = cap;
     }
     memcpy(g_listed_host, pair_base, sizeof(pair_base));
@@ -922,28 +965,82 @@ int process_paf_listed(ekp_ctx* c, long long npk, int p3, const float* peaks, in
     const double t1 = trace ? now_us() : 0.0;
     cudaStream_t st = nullptr;
     if (c->has_run && c->last_stream != st) CU(cudaStreamWaitEvent(st, c->done, 0));
-    CU(cudaMemcpyAsync(g_listed_dev, g_listed_host, bytes, cudaMemcpyHostToDevice, st));
-    mark(c, 0, st);
-    mark(c, 1, st);
     int rc = EKP_OK;
-    if (npk <= peaks_one_max()) {   // ingest + sort in one block, no counters to clear
-        CU(launch_peaks_ingest_sort_one(reinterpret_cast<const float*>(g_listed_dev + off_peaks), (int) npk, p3, f2, f1, c->max_peaks, c->max_part,
-                                        c->line, c->part_off, c->n_peaks, c->raw_count, c->overflow, st));
-        c->launches += 1;
-    } else {
-        CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
-        CU(launch_peaks_ingest(reinterpret_cast<const float*>(g_listed_dev + off_peaks), nullptr, (int) npk, (int) npk, p3, 1, f2, f1, c->raw,
-                               c->raw_count, c->max_peaks, c->overflow, st));
-        c->launches += 1;
-        rc = run_peak_sort(c, 1, /*id_from_key=*/1, st);
-        if (rc) return rc;
-    }
     PafSource src;
     src.layout = EKP_LAYOUT_NHWC; src.H = f1; src.W = f2; src.C = f3; src.h = f1 / 8; src.w = f2 / 8; src.ids_are_rows = 0;
     src.ptr = reinterpret_cast<const float*>(g_listed_dev + off_samp); src.mode = PAF_PACKED;
     src.pair_base = reinterpret_cast<const int*>(g_listed_dev);
-    rc = run_connect_assemble(c, 1, src, h1, st);
-    if (rc) return rc;
+    bool launched = false;
+    if (tiny) {
+        const bool as_graph = tiny_mode == TINY_ZC_GRAPH;
+        unsigned char* blk = g_listed_host_dev;   // the kernels read the pinned block itself
+        PafSource tsrc = src;
+        tsrc.ptr = reinterpret_cast<const float*>(blk + off_samp);
+        tsrc.pair_base = reinterpret_cast<const int*>(blk);
+        unsigned char* rec_direct = c->h_records_dev;
+        auto enqueue = [&](cudaStream_t q) -> int {   // the three kernels on `q`
+            CU(launch_peaks_ingest_sort_one(reinterpret_cast<const float*>(blk + off_peaks), 0, reinterpret_cast<const int*>(blk) + 31, p3, f2, f1,
+                                            c->max_peaks, c->max_part, c->line, c->part_off, c->n_peaks, c->raw_count, c->overflow, q));
+            return run_connect_assemble(c, 1, tsrc, h1, q, rec_direct);
+        };
+        if (!as_graph) {
+            rc = enqueue(st);
+            if (rc) return rc;
+            c->launches += 1;
+            launched = true;
+        } else {
+            TinyGraph* hit = nullptr;
+            for (size_t i = 0; i < g_tiny.size();) {   // graphs of a context that no longer exists go
+                if (g_tiny[i].ctx_serial != c->serial) { cudaGraphExecDestroy(g_tiny[i].exec); g_tiny.erase(g_tiny.begin() + (long) i); }
+                else i++;
+            }
+            for (TinyGraph& e : g_tiny)
+                if (e.p3 == p3 && e.f1 == f1 && e.f2 == f2 && e.f3 == f3 && e.h1 == h1 && e.bytes == bytes) hit = &e;
+            if (!hit) {
+                if (!c->cap_stream) CU(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+                const long long before = c->launches;
+                cudaGraph_t graph = nullptr;
+                cudaGraphExec_t exec = nullptr;
+                CU(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+                const int rc2 = enqueue(c->cap_stream);
+                cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+                if (rc2 == EKP_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                c->launches = before;
+                if (rc2 != EKP_OK || ce != cudaSuccess || !exec) { cudaGetLastError(); g_tiny_ok = false; }   // stay on the general path from now on
+                else {
+                    if (g_tiny.size() >= 8) { cudaGraphExecDestroy(g_tiny.front().exec); g_tiny.erase(g_tiny.begin()); }
+                    g_tiny.push_back(TinyGraph{c->serial, p3, f1, f2, f3, h1, bytes, exec});
+                    hit = &g_tiny.back();
+                }
+            }
+            if (hit) {
+                CU(cudaGraphLaunch(hit->exec, st));
+                c->launches += 3;
+                c->graph_launches += 1;
+                launched = true;
+            }
+        }
+    }
+    if (!launched) {
+        CU(cudaMemcpyAsync(g_listed_dev, g_listed_host, bytes, cudaMemcpyHostToDevice, st));
+        mark(c, 0, st);
+        mark(c, 1, st);
+        if (npk <= peaks_one_max()) {   // ingest + sort in one block, no counters to clear
+            CU(launch_peaks_ingest_sort_one(reinterpret_cast<const float*>(g_listed_dev + off_peaks), (int) npk, nullptr, p3, f2, f1, c->max_peaks,
+                                            c->max_part, c->line, c->part_off, c->n_peaks, c->raw_count, c->overflow, st));
+            c->launches += 1;
+        } else {
+            CU(cudaMemsetAsync(c->raw_count, 0, sizeof(int) * 2 * (size_t) c->max_batch, st));
+            CU(launch_peaks_ingest(reinterpret_cast<const float*>(g_listed_dev + off_peaks), nullptr, (int) npk, (int) npk, p3, 1, f2, f1, c->raw,
+                                   c->raw_count, c->max_peaks, c->overflow, st));
+            c->launches += 1;
+            rc = run_peak_sort(c, 1, /*id_from_key=*/1, st);
+            if (rc) return rc;
+        }
+        rc = run_connect_assemble(c, 1, src, h1, st);
+        if (rc) return rc;
+    }
     rc = finish_submit(c, 1, st);
     if (rc) return rc;
     const double t2 = trace ? now_us() : 0.0;

@@ -806,7 +806,9 @@ cudaError_t launch_debug_std_sort(float* scores, unsigned* tags, int n, unsigned
 // ---- launch ------------------------------------------------------------------------------------------------
 // Gathers: 8-byte ones when the tensor is channel-last, even and aligned.  Threads: blocks are latency-bound chains; a
 // batch whose 19 x n blocks all fit on the GPU at once (crowded scenes come in small batches) gets twice the threads per
-// block, bigger batches keep more blocks resident instead.
+// block, bigger batches keep more blocks resident instead.  (512 threads for those small batches: 16 x 1312x736 with 20 / 35 /
+// 50 / 80 people at capacities 256 / 4096: 24.3 / 47.2 / 102 / 393 us against 26.6 / 51.0 / 116 / 443 us, but nothing on the
+// bench's crowded configuration (capacities 128 / 1024: 59.4 vs 59.4 us dense, 55.2 vs 53.2 us reference front-end); not kept.)
 constexpr size_t kSmemPerSm = 227 * 1024;
 
 template <int kSrc, int kT>
@@ -816,7 +818,6 @@ static cudaError_t launch_one(const ConnectParams& P, int n, size_t smem, cudaSt
 }
 template <int kSrc>
 static cudaError_t launch_src(const ConnectParams& P, int n, size_t smem, int threads, cudaStream_t stream) {
-    if (threads == 512) return launch_one<kSrc, 512>(P, n, smem, stream);
     if (threads == 256) return launch_one<kSrc, 256>(P, n, smem, stream);
     return launch_one<kSrc, 128>(P, n, smem, stream);
 }
@@ -827,8 +828,8 @@ cudaError_t configure_connect(int max_part, int max_cand) {
     if (big > kSmemPerSm) return cudaErrorInvalidValue;
     cudaError_t e = cudaSuccess;
 #define EKP_RAISE(S, T) if (e == cudaSuccess) e = raise_dynamic_smem_limit(paf_connect_kernel<S, T>, big)
-    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256); EKP_RAISE(SRC_GLOBAL, 512);
-    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256); EKP_RAISE(SRC_GLOBAL_VEC2, 512);
+    EKP_RAISE(SRC_GLOBAL, 128); EKP_RAISE(SRC_GLOBAL, 256);
+    EKP_RAISE(SRC_GLOBAL_VEC2, 128); EKP_RAISE(SRC_GLOBAL_VEC2, 256);
 #undef EKP_RAISE
     return e;
 }
@@ -840,8 +841,7 @@ cudaError_t launch_paf_connect(const ConnectParams& P_in, int n, cudaStream_t st
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = connect_smem_bytes(P.max_part, P.max_cand);
-    static const int env_crowd_threads = getenv("EKP_CONN_CROWD_THREADS") ? atoi(getenv("EKP_CONN_CROWD_THREADS")) : 2 * kConnThreads;
-    const int threads = EKP_NUM_LIMB * n <= 4 * sms ? env_crowd_threads : kConnThreads;
+    const int threads = EKP_NUM_LIMB * n <= 4 * sms ? 2 * kConnThreads : kConnThreads;
     // per-block regimes (same results in both): up to six rounds of ten-lanes-per-pair scoring, beyond that one thread per
     // pair in two exact passes
     static const int env_by_sample = getenv("EKP_BY_SAMPLE_MAX_PAIRS") ? atoi(getenv("EKP_BY_SAMPLE_MAX_PAIRS")) : -1;

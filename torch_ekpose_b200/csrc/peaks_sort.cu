@@ -105,10 +105,12 @@ __global__ void __launch_bounds__(kSortThreads) peaks_sort_kernel(const RawPeak*
 // image's overflow word, so the call needs no cudaMemsetAsync in front.
 constexpr int kOneThreads = 256;
 constexpr int kOneMaxPeaks = 4096;
-__global__ void __launch_bounds__(kOneThreads) peaks_ingest_sort_one_kernel(const float* __restrict__ peaks, int npk, int p3, int W, int H,
-                                                                            int raw_cap, int max_part, ekp_peak* __restrict__ line,
-                                                                            int* __restrict__ part_off, int* __restrict__ n_peaks,
-                                                                            int* __restrict__ raw_count, unsigned* __restrict__ overflow) {
+__global__ void __launch_bounds__(kOneThreads) peaks_ingest_sort_one_kernel(const float* __restrict__ peaks, int npk, const int* __restrict__ npk_dev,
+                                                                            int p3, int W, int H, int raw_cap, int max_part,
+                                                                            ekp_peak* __restrict__ line, int* __restrict__ part_off,
+                                                                            int* __restrict__ n_peaks, int* __restrict__ raw_count,
+                                                                            unsigned* __restrict__ overflow) {
+    if (npk_dev) npk = max(*npk_dev, 0);   // the count travels with the peaks (a replayed CUDA graph has constant arguments)
     __shared__ unsigned short sKey[kOneMaxPeaks];   // input indices, bucketed by part
     __shared__ unsigned char sPart[kOneMaxPeaks];
     __shared__ int sCount[EKP_NUM_PART + 1], sBase[EKP_NUM_PART + 2], sFill[EKP_NUM_PART + 1];
@@ -163,10 +165,10 @@ __global__ void __launch_bounds__(kOneThreads) peaks_ingest_sort_one_kernel(cons
     overflow[0] = ovf;
 }
 int peaks_one_max() { return kOneMaxPeaks; }
-cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, int p3, int W, int H, int raw_cap, int max_part, ekp_peak* line,
-                                         int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream) {
-    peaks_ingest_sort_one_kernel<<<1, kOneThreads, 0, stream>>>(peaks, npk, p3, W, H, raw_cap, max_part, line, part_off, n_peaks, raw_count,
-                                                               overflow);
+cudaError_t launch_peaks_ingest_sort_one(const float* peaks, int npk, const int* npk_dev, int p3, int W, int H, int raw_cap, int max_part,
+                                         ekp_peak* line, int* part_off, int* n_peaks, int* raw_count, unsigned* overflow, cudaStream_t stream) {
+    peaks_ingest_sort_one_kernel<<<1, kOneThreads, 0, stream>>>(peaks, npk, npk_dev, p3, W, H, raw_cap, max_part, line, part_off, n_peaks,
+                                                               raw_count, overflow);
     return cudaGetLastError();
 }
 
