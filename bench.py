@@ -50,8 +50,8 @@ BATCHES_PER_STEP = int(os.environ.get("EKP_BENCH_BATCHES_PER_STEP", "32"))
 H_LO, W_LO = 46, 54     # stride-8 map of a 368x432 image
 PEOPLE = (1, 6)
 INPUT_SETS = 4          # distinct input batches rotated between batches
-N_CTX = int(os.environ.get("EKP_BENCH_CONTEXTS", "4"))   # contexts / CUDA streams the batches rotate over
-N_CTX_CFG = int(os.environ.get("EKP_BENCH_CFG_CONTEXTS", "4"))   # ... in the configs[2] / configs[3] context legs
+N_CTX = int(os.environ.get("EKP_BENCH_CONTEXTS", "8"))   # contexts / CUDA streams the batches rotate over
+N_CTX_CFG = int(os.environ.get("EKP_BENCH_CFG_CONTEXTS", "8"))   # ... in the configs[2] / configs[3] context legs
 
 
 def algo_bytes(h, w, materialize=True):
@@ -387,8 +387,10 @@ def pin_rank(local_rank, local_world):
 class Runner:
     """N_CTX contexts on N_CTX streams taking batches of one configuration in turn."""
 
-    def __init__(self, ek, torch, dev, local_rank, n, h, w, people, seed, max_peaks, max_humans, max_part, max_cand, nctx=N_CTX, nsets=INPUT_SETS):
+    def __init__(self, ek, torch, dev, local_rank, n, h, w, people, seed, max_peaks, max_humans, max_part, max_cand, nctx=N_CTX, nsets=INPUT_SETS,
+                 mat_nctx=None):
         self.ek, self.torch, self.dev = ek, torch, dev
+        self.mat_nctx = min(nctx, mat_nctx or nctx)   # contexts the MATERIALISING batches rotate over (each holds n x 65 x the input bytes)
         self.n, self.h, self.w = n, h, w
         self.syn = load_synthetic()
         self.host, self.devs = [], []
@@ -402,7 +404,7 @@ class Runner:
         self.main = torch.cuda.current_stream(dev)
 
     def submit(self, i, frontend, materialize, inputs=None):
-        k = i % len(self.pps)
+        k = i % (self.mat_nctx if materialize else len(self.pps))
         hd, pd = (inputs or self.devs)[i % len(self.devs)]
         self.pps[k].run(hd, pd, layout="nchw", frontend=frontend, materialize=materialize, stream=self.streams[k])
 
@@ -680,7 +682,7 @@ def run_ours(args, rank, local_rank, world):
     def measure(run, name, workload, frontend, materialize, batches, check):
         ips, ms_b = run.throughput(frontend, materialize, batches)
         st = run.isolated_stage_ms(frontend, materialize)
-        ent = {"workload": workload, "contexts": len(run.pps), "images_per_s_per_gpu": ips, "ms_per_batch_pipelined": ms_b, "stage_ms_isolated": st,
+        ent = {"workload": workload, "contexts": run.mat_nctx if materialize else len(run.pps), "images_per_s_per_gpu": ips, "ms_per_batch_pipelined": ms_b, "stage_ms_isolated": st,
                "stages_4_5_ms_isolated": st["peak_sort"] + st["connect"] + st["assemble"],
                "roofline": roofline_entry(frontend, run.n, run.h, run.w, materialize, st, peak, peak_src, consts, clk.get("sm_mhz"))}
         if check and rank == 0:
@@ -696,7 +698,7 @@ def run_ours(args, rank, local_rank, world):
     if not args.headline_only:
         # configs[2]: 656x368 frames, batch 256
         R3 = Runner(ek, torch, dev, local_rank, 256, 46, 82, (2, 8), seed=300 + 7 * rank, max_peaks=1024, max_humans=32, max_part=64,
-                    max_cand=512, nctx=N_CTX_CFG, nsets=2)
+                    max_cand=512, nctx=N_CTX_CFG, nsets=2, mat_nctx=4)
         measure(R3, "c3_656x368_x256_dense_materialised", "configs[2]: 656x368, batch 256, dense front-end + operator-surface tensors", "dense", True, 12, True)
         measure(R3, "c3_656x368_x256_dense_lean", "configs[2] without materialisation", "dense", False, 40, False)
         measure(R3, "c3_656x368_x256_reference_lean", "configs[2], reference front-end", "reference", False, 40, True)
@@ -704,7 +706,7 @@ def run_ours(args, rank, local_rank, world):
         R3.close()
         # configs[3]: crowded 1312x736, 30-40 people, batch 16
         R4 = Runner(ek, torch, dev, local_rank, 16, 92, 164, (30, 40), seed=400 + 7 * rank, max_peaks=2048, max_humans=128, max_part=128,
-                    max_cand=1024, nctx=N_CTX_CFG, nsets=2)
+                    max_cand=1024, nctx=N_CTX_CFG, nsets=2, mat_nctx=4)
         measure(R4, "c4_1312x736_x16_crowded_dense_materialised", "configs[3]: 1312x736, 30-40 people, batch 16, dense front-end + operator-surface tensors", "dense", True, 30, True)
         measure(R4, "c4_1312x736_x16_crowded_dense_lean", "configs[3] without materialisation", "dense", False, 60, True)
         measure(R4, "c4_1312x736_x16_crowded_reference_lean", "configs[3], reference front-end", "reference", False, 60, True)
