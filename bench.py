@@ -680,6 +680,7 @@ def run_ours(args, rank, local_rank, world):
     configs = {}
 
     def measure(run, name, workload, frontend, materialize, batches, check):
+        barrier()   # every rank measures the same leg at the same time (a rank still in its previous phase disturbs the host side of the others)
         ips, ms_b = run.throughput(frontend, materialize, batches)
         st = run.isolated_stage_ms(frontend, materialize)
         ent = {"workload": workload, "contexts": run.mat_nctx if materialize else len(run.pps), "images_per_s_per_gpu": ips, "ms_per_batch_pipelined": ms_b, "stage_ms_isolated": st,
