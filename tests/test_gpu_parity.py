@@ -117,6 +117,36 @@ def test_process_paf_stream_of_frames(ek):
             assert np.float32(ek.pafprocess.get_part_score(cid)).view(np.uint32) == np.float32(line[2][cid]).view(np.uint32)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_process_paf_host_entry_fuzz(ek, seed):
+    """The host-pointer operator surface on adversarial scenes (piecewise-constant PAF: exact score ties, merges, connections
+    across people; fractional and border coordinates, which the sample positions' float arithmetic sees), sized to take each
+    of its routes: the zero-copy graph (a few people), the listed upload (dozens), positions listed by a kernel (a crowd).
+    People, scores and the getter table against the compiled reference."""
+    rng = np.random.default_rng(4100 + seed)
+    H, W = 128, 192
+    for people, drop, block, levels in [(1, 0.0, 8, [1.0]), (3, 0.0, 8, [0.0, 1.0]), (5, 0.2, 16, [-1.0, 0.0, 0.5, 1.0]), (2, 0.5, 4, [0.5, 1.0]),
+                                        (14, 0.3, 16, [0.0, 0.25, 1.0]), (30, 0.15, 8, [0.0, 0.25, 1.0]), (70, 0.2, 4, [-0.5, 0.0, 0.5, 1.0])]:
+        peaks, paf = _fuzz_scene(rng, H, W, people, drop, block, levels)
+        if len(peaks) == 0:
+            continue
+        peaks = peaks.copy()
+        frac = rng.random(len(peaks)) < 0.3   # the reference truncates float coordinates (pafprocess.cpp:30-31)
+        peaks[frac, 0] = np.minimum(peaks[frac, 0] + rng.random(int(frac.sum())).astype(np.float32) * 0.99, np.float32(W - 1))
+        peaks[frac, 1] = np.minimum(peaks[frac, 1] + rng.random(int(frac.sum())).astype(np.float32) * 0.99, np.float32(H - 1))
+        edge = rng.random(len(peaks)) < 0.1
+        peaks[edge, 0] = rng.choice([0.0, W - 1.0], int(edge.sum()))
+        sub, line = util.oracle_people(peaks, H, W, paf)
+        assert ek.pafprocess.process_paf(peaks[None], np.zeros((H, W, 19), np.float32), paf) == 0
+        n, cids, scores = _compat_subset(ek)
+        assert n == len(sub), f"{people} people: {n} vs {len(sub)}"
+        assert np.array_equal(cids, sub[:, :18].astype(np.int32)), f"{people} people"
+        if n:
+            assert_bits_equal(scores, (sub[:, 18] / sub[:, 19]).astype(np.float32), "human score")
+        for cid in range(0, len(peaks), 11):
+            assert ek.pafprocess.get_part_x(cid) == int(line[0][cid]) and ek.pafprocess.get_part_y(cid) == int(line[1][cid])
+
+
 def test_process_paf_pools_all_p1_images(ek):
     """peaks[p1, p2, p3]: the reference walks every (p1, p2) row into ONE peak list (pafprocess.cpp:26-36)."""
     g = golden("c2_46x54_p6")
