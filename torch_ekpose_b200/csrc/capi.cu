@@ -24,6 +24,7 @@ int dense_frontend_tile_wl(int w);
 cudaError_t configure_dense_frontend();
 cudaError_t configure_dense_plane(int max_h, int max_w);
 cudaError_t set_interior_taps(const float* taps64);
+cudaError_t set_cubic_table(const float* tab32);
 cudaError_t launch_dense_frontend(const DenseParams& p, cudaStream_t stream);
 cudaError_t launch_ref_frontend(const RefParams& p, cudaStream_t stream);
 int ref_frontend_launches(int refine);
@@ -294,6 +295,7 @@ extern "C" int ekp_create_ex(ekp_ctx** out, int device, int max_batch, int max_h
     float cubic[32];
     build_cubic_table(cubic);
     e = cudaMemcpy(c->cubic, cubic, sizeof(cubic), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = set_cubic_table(cubic);
     double gauss[13];
     build_scipy_gauss3(gauss);
     if (e == cudaSuccess) e = cudaMemcpy(c->gauss, gauss, sizeof(gauss), cudaMemcpyHostToDevice);

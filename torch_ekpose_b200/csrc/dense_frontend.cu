@@ -520,6 +520,49 @@ __device__ __forceinline__ void nms_task_at(const DenseParams& p, int img, int c
     NmsState st;
     st.hm2 = NEG_INF; st.hm1 = NEG_INF; st.s1 = NEG_INF;
     const int Ytop = 8 * m0 - 1;
+    if (!kDebug && m0 >= 3 && m0 + tb <= h - 3) {
+        // Interior task (most of a map): every window, the halo rows' included, is row block m's own five rows m - 2 .. m + 2
+        // and the next one is the previous one shifted by a row; the halo rows 8 m0 - 1 and 8 (m0 + tb) are interior rows too,
+        // so their taps are phases 7 and 0 of the constant-bank table (ensure_tables checks that the table in global memory
+        // repeats it there).  Same operations as the general walk below without its window bookkeeping and global loads.
+        auto interior_row = [&](int k) -> float {
+            float acc = __fmul_rn(cTapsInterior[k][0], T0);
+            acc = fmaf(cTapsInterior[k][1], T1, acc);
+            acc = fmaf(cTapsInterior[k][2], T2, acc);
+            acc = fmaf(cTapsInterior[k][3], T3, acc);
+            acc = fmaf(cTapsInterior[k][4], T4, acc);
+            return acc;
+        };
+        T0 = trow(m0 - 3); T1 = trow(m0 - 2); T2 = trow(m0 - 1); T3 = trow(m0); T4 = trow(m0 + 1);
+        {
+            const float acc = interior_row(7);
+            nms_row(st, inb ? acc : NEG_INF, X, Ytop, false, p.thr, c, sink);
+            st.s1 = NEG_INF;
+        }
+        for (int b = 0; b < tb; b++) {
+            const int m = m0 + b;
+            T0 = T1; T1 = T2; T2 = T3; T3 = T4; T4 = trow(m + 2);
+            float bound = __fmul_rn(cTapsInteriorMax[0], fmaxf(T0, 0.f));
+            bound = fmaf(cTapsInteriorMax[1], fmaxf(T1, 0.f), bound);
+            bound = fmaf(cTapsInteriorMax[2], fmaxf(T2, 0.f), bound);
+            bound = fmaf(cTapsInteriorMax[3], fmaxf(T3, 0.f), bound);
+            bound = fmaf(cTapsInteriorMax[4], fmaxf(T4, 0.f), bound);
+            if (!__any_sync(0xffffffffu, inb && bound > p.thr * 0.9999f)) {
+                nms_row(st, NEG_INF, X, 8 * m, out_lane, p.thr, c, sink);
+                st.hm2 = NEG_INF; st.hm1 = NEG_INF; st.s1 = NEG_INF;
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float acc = interior_row(k);
+                nms_row(st, inb ? acc : NEG_INF, X, 8 * m + k, out_lane, p.thr, c, sink);
+            }
+        }
+        T0 = T1; T1 = T2; T2 = T3; T3 = T4; T4 = trow(m0 + tb + 2);
+        const float accb = interior_row(0);
+        nms_row(st, inb ? accb : NEG_INF, X, 8 * (m0 + tb), out_lane, p.thr, c, sink);
+        return;
+    }
     if (Ytop >= 0) {  // halo row above the task's rows: contributes its horizontal max only
         window(m0 - 1);
         const float acc = row_generic(Ytop);
@@ -732,8 +775,11 @@ constexpr int kPlaneThreads = 256;
 __host__ __device__ inline int plane_pairs(int h) { return (h + kTaskTB - 1) / kTaskTB; }
 __host__ __device__ inline void plane_slice_rows(int h, int slices, int slice, int& rp_lo, int& rp_hi, int& r_lo, int& r_hi) {
     const int nrp = plane_pairs(h);
-    rp_lo = (int) ((long long) nrp * slice / slices);
-    rp_hi = (int) ((long long) nrp * (slice + 1) / slices);
+    if (slices == 1) { rp_lo = 0; rp_hi = nrp; }   // (the usual case: no 64-bit divisions in every thread)
+    else {
+        rp_lo = (int) ((long long) nrp * slice / slices);
+        rp_hi = (int) ((long long) nrp * (slice + 1) / slices);
+    }
     const int m0 = rp_lo * kTaskTB, m1 = min(rp_hi * kTaskTB, h);   // row blocks [m0, m1)
     r_lo = max(min(m0 - 3, h - 5), 0);                             // staged rows: the windows of the rows and their halo rows
     r_hi = min(max(m1 + 2, 4), h - 1);
@@ -787,20 +833,25 @@ __global__ void __launch_bounds__(kPlaneThreads) dense_plane_kernel(const DenseP
         __syncthreads();
     }
     const float* base = sRows - r_lo * w;   // base[j * w + i] = sample (row j, column i) of the map, j in [r_lo, r_hi]
+    // idx / nstrips as one multiply-high: exact while idx * nstrips < 2^32 (both are below 2^16: the task list holds shorts)
+    const unsigned div_ns = 0xffffffffu / (unsigned) nstrips + 1u;
     // M[r][s]: what row r can contribute to strip s at most (the columns a strip's lanes read: build_task_list)
     for (int idx = threadIdx.x; idx < nrows * nstrips; idx += kPlaneThreads) {
-        const int r = idx / nstrips, strip = idx - r * nstrips;
+        const int r = (int) __umulhi((unsigned) idx, div_ns), strip = idx - r * nstrips;
         const int Xa = -1 + 30 * strip;
         const int xlo = min(max(Xa, 0), W - 1), xhi = min(max(Xa + 31, 0), W - 1);
         const int c_lo = min(max((xlo >> 3) - 2, 0), w - 5), c_hi = min(max((xhi >> 3) - 2, 0), w - 5) + 4;
         float mx = 0.f;
-        for (int i = c_lo; i <= c_hi; i++) mx = fmaxf(mx, sRows[r * w + i]);
+        const float* rowp = sRows + r * w;
+#pragma unroll
+        for (int k = 0; k < 9; k++) mx = fmaxf(mx, rowp[min(c_lo + k, c_hi)]);   // 5..9 columns (a strip spans <= 5 stride-8 cells + 4): straight-line code
         sM[idx] = mx;
     }
     __syncthreads();
     // exact early-out per (row-block pair, strip): same bounds as build_task_list
     for (int t = threadIdx.x; t < ntask; t += kPlaneThreads) {
-        const int rp = rp_lo + t / nstrips, strip = t % nstrips;
+        const int q = (int) __umulhi((unsigned) t, div_ns);
+        const int rp = rp_lo + q, strip = t - q * nstrips;
         const int b_lo = rp * kTaskTB, b_hi = min(b_lo + kTaskTB, h);
         bool active = !(p.thr > 0.f);
         for (int m = b_lo; m < b_hi && !active; m++) {
@@ -824,7 +875,8 @@ __global__ void __launch_bounds__(kPlaneThreads) dense_plane_kernel(const DenseP
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nactive) break;
         const int t = sList[item];
-        const int rp = rp_lo + t / nstrips, strip = t % nstrips;
+        const int q = (int) __umulhi((unsigned) t, div_ns);
+        const int rp = rp_lo + q, strip = t - q * nstrips;
         const int m0 = rp * kTaskTB;
         nms_task_at<false, 1>(p, img, c, strip, m0, min(kTaskTB, h - m0), 0, W, base, w, sTaps);
     }

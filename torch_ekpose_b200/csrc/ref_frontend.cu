@@ -20,6 +20,12 @@ namespace ekp {
 
 constexpr int kRefWarps = 8;
 
+// cv2's bicubic coefficients for the eight x8 phases t = (2k + 1) / 16 (capi.cu build_cubic_table): the vertical pass of
+// ref_refine_kernel reads them as constant-bank operands; the horizontal pass (a different phase per lane) keeps the copy
+// in global memory (RefParams::cubic).
+__constant__ float cCubic[8][4];
+cudaError_t set_cubic_table(const float* tab32) { return cudaMemcpyToSymbol(cCubic, tab32, sizeof(float) * 32); }
+
 // ---- find_peaks: one block per (part, image) ----------------------------------------------------------------------------
 // Writes one RawPeak per maximum: with p.refine == 0 already in its final form (NMS(bool_refine_center=False): the
 // maximum itself at (c + 0.5) * 8 - 0.5 truncated, heat value as score), else the stride-8 cell (x, y) for
@@ -163,29 +169,41 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_refine_kernel(const RefPar
         }
     }
     __syncwarp();
-    // vertical pass (VResizeCubicVec_32f order) fused with the arg-max: first maximum in row-major order
+    // vertical pass (VResizeCubicVec_32f order) fused with the arg-max: first maximum in row-major order.  Eight output rows
+    // per source row: output row 8 yb + k has phase (k + 4) & 7 and reads the four rows around sy = yb - 1 (k < 4) or yb
+    // (k >= 4), so inside the unrolled block the coefficients are constant-bank operands and the row pointers are set up
+    // twice per eight rows.  A lane meets its elements in increasing row-major index (row by row, slot 0 before slot 1), so
+    // "first maximum" within a lane is a strict > against what it holds; the lanes' results are merged with the index
+    // tie-break below.  (Before: coefficients loaded per row, pointers per row, a three-way test per element: 12.2 M -> see
+    // profiles/README.md.)
     float best = -INFINITY;
-    int best_idx = 0x7fffffff;
-    for (int dy = 0; dy < H8; dy++) {
-        const int q = dy + 4;
-        const int sy = (q >> 3) - 1;
-        const float* b = p.cubic + (q & 7) * 4;   // warp-uniform
-        const float b0 = __ldg(b + 0), b1 = __ldg(b + 1), b2 = __ldg(b + 2), b3 = __ldg(b + 3);
-        const float* T3 = sTmp[warp] + min(max(sy + 2, 0), ph - 1) * 40;
-        const float* T2 = sTmp[warp] + min(max(sy + 1, 0), ph - 1) * 40;
-        const float* T1 = sTmp[warp] + min(max(sy, 0), ph - 1) * 40;
-        const float* T0 = sTmp[warp] + min(max(sy - 1, 0), ph - 1) * 40;
+    int best_idx = lane < W8 ? lane : 0x7fffffff;   // the first element (row 0) stands until something is greater
+    for (int yb = 0; yb < ph; yb++) {
+        const float* Tm2 = sTmp[warp] + min(max(yb - 2, 0), ph - 1) * 40;
+        const float* Tm1 = sTmp[warp] + min(max(yb - 1, 0), ph - 1) * 40;
+        const float* Tz = sTmp[warp] + yb * 40;
+        const float* Tp1 = sTmp[warp] + min(yb + 1, ph - 1) * 40;
+        const float* Tp2 = sTmp[warp] + min(yb + 2, ph - 1) * 40;
 #pragma unroll
-        for (int sl = 0; sl < 2; sl++) {
-            const int dx = 32 * sl + lane;
-            if (dx < W8) {
-                float v = __fmul_rn(T3[dx], b3);
-                v = __fadd_rn(__fmul_rn(T2[dx], b2), v);
-                v = __fadd_rn(__fmul_rn(T1[dx], b1), v);
-                v = __fadd_rn(__fmul_rn(T0[dx], b0), v);
-                if (kGauss) { sV[dy * 40 + dx] = v; continue; }
-                const int idx = dy * W8 + dx;
-                if (v > best || (v == best && idx < best_idx) || best_idx == 0x7fffffff) { best = v; best_idx = idx; }
+        for (int k = 0; k < 8; k++) {
+            const int phs = (k + 4) & 7;
+            // sy = yb - 1 (k < 4): rows sy - 1 .. sy + 2 = yb - 2 .. yb + 1;  sy = yb (k >= 4): yb - 1 .. yb + 2
+            const float* T0 = k < 4 ? Tm2 : Tm1;
+            const float* T1 = k < 4 ? Tm1 : Tz;
+            const float* T2 = k < 4 ? Tz : Tp1;
+            const float* T3 = k < 4 ? Tp1 : Tp2;
+            const int dy = 8 * yb + k;
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int dx = 32 * sl + lane;
+                if (dx < W8) {
+                    float v = __fmul_rn(T3[dx], cCubic[phs][3]);
+                    v = __fadd_rn(__fmul_rn(T2[dx], cCubic[phs][2]), v);
+                    v = __fadd_rn(__fmul_rn(T1[dx], cCubic[phs][1]), v);
+                    v = __fadd_rn(__fmul_rn(T0[dx], cCubic[phs][0]), v);
+                    if (kGauss) { sV[dy * 40 + dx] = v; continue; }
+                    if (v > best) { best = v; best_idx = dy * W8 + dx; }
+                }
             }
         }
     }
