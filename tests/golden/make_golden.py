@@ -199,7 +199,10 @@ def nms_gauss_fixture():
         jl = p2p.NMS(heat, upsampFactor=cfg.MODEL.DOWNSAMPLE, bool_gaussian_filt=True, config=cfg)
         rows = [tuple(pk) + (jt,) for jt, jp in enumerate(jl) for pk in jp]
         d[name + "_peaks"] = np.array(rows, np.float64).reshape(-1, 5)
-        plain = sum(len(jp) for jp in p2p.NMS(heat, upsampFactor=cfg.MODEL.DOWNSAMPLE, config=cfg))
+        jl0 = p2p.NMS(heat, upsampFactor=cfg.MODEL.DOWNSAMPLE, config=cfg)
+        plain = sum(len(jp) for jp in jl0)
+        if name == "border":   # the clipped windows through the plain refinement as well (the scenes' own fixtures hold theirs)
+            d["border_peaks_plain"] = np.array([tuple(pk) + (jt,) for jt, jp in enumerate(jl0) for pk in jp], np.float64).reshape(-1, 5)
         print("nms_gauss", name, "peaks", len(rows), "(without the filter:", plain, ")")
     cv2.ipp.setUseIPP(True)
     np.savez_compressed(os.path.join(OUT, "nms_gauss.npz"), **d)

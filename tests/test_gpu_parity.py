@@ -248,6 +248,11 @@ def test_nms_with_gaussian_filter_dropin(ek, scene):
     flat = np.array([tuple(r) + (k,) for k, rows in enumerate(lists) for r in rows], np.float64).reshape(-1, 5)
     assert_bits_equal(flat, g[scene + "_peaks"], "NMS(bool_gaussian_filt=True) joint list vs the reference's")
     assert_bits_equal(flat.astype(np.float32), util.frontend().ref_nms(heat, gauss=True), "vs the oracle")
+    if scene == "border":   # the same clipped windows through the plain refinement, against the reference's own output
+        plain = ek.NMS(heat, upsampFactor=8, config=ek.cfg)
+        flat0 = np.array([tuple(r) + (k,) for k, rows in enumerate(plain) for r in rows], np.float64).reshape(-1, 5)
+        assert_bits_equal(flat0, g["border_peaks_plain"], "NMS() on the border map vs the reference's")
+        assert (flat0[:, :2] != flat[:, :2]).any() or (flat0[:, 2] != flat[:, 2]).any()   # the filter does change something
     # the filter has no effect without refinement (:103-122), as in the reference
     a = ek.NMS(heat, upsampFactor=8, bool_refine_center=False, bool_gaussian_filt=True, config=ek.cfg)
     b = ek.NMS(heat, upsampFactor=8, bool_refine_center=False, config=ek.cfg)
