@@ -920,8 +920,8 @@ int process_paf_listed(ekp_ctx* c, long long npk, int p3, const float* peaks, in
         if (graphs_off && m == TINY_ZC_GRAPH) m = TINY_ZC;
         return m;
     }();
-    const bool tiny = tiny_mode != TINY_OFF && g_tiny_ok && !c->timing && c->h_records_dev && npk <= kTinyPeaks && npk <= peaks_one_max() &&
-                      nsamples <= kTinyMaxSamples;
+    bool tiny = tiny_mode != TINY_OFF && g_tiny_ok && !c->timing && c->h_records_dev && npk <= kTinyPeaks && npk <= peaks_one_max() &&
+                nsamples <= kTinyMaxSamples;
     long long samp_class = 2048;
     while (samp_class < nsamples) samp_class *= 2;
     pair_base[31] = (int) npk;
@@ -936,9 +936,10 @@ int process_paf_listed(ekp_ctx* c, long long npk, int p3, const float* peaks, in
         const size_t cap = bytes + bytes / 2 + 4096;
         CU(cudaMallocHost((void**) &g_listed_host, cap));
         CU(cudaMalloc((void**) &g_listed_dev, cap));
-        CU(cudaHostGetDevicePointer((void**) &g_listed_host_dev, g_listed_host, 0));
+        if (cudaHostGetDevicePointer((void**) &g_listed_host_dev, g_listed_host, 0) != cudaSuccess) { cudaGetLastError(); g_listed_host_dev = nullptr; }
         g_listed_cap = cap;
     }
+    if (!g_listed_host_dev) tiny = false;   // pinned memory the device cannot address (no unified addressing): the copying path
     memcpy(g_listed_host, pair_base, sizeof(pair_base));
     memcpy(g_listed_host + off_peaks, peaks, sizeof(float) * (size_t) npk * p3);
     float2* samp = reinterpret_cast<float2*>(g_listed_host + off_samp);
