@@ -443,7 +443,7 @@ static int enqueue_batch(ekp_ctx* c, const PostArgs& a, cudaStream_t st, int* ke
         k += 1;
         // Stage 4 evaluates the bilinear expression of the materialising kernel on the stride-8 PAF (bit-identical to
         // reading the materialised paf_mat[y][x], tests/test_gpu_parity.py: lean == materialised): the stride-8 planes
-        // are L2- (or shared-memory-) resident, while gathers from the 36 MB-per-image paf_mat go to DRAM.
+        // are L2-resident, while gathers from the 36 MB-per-image paf_mat go to DRAM.
         // EKP_CONNECT_FROM_MAT=1 reads paf_mat instead, exactly as the reference's process_paf does.
         static const bool from_mat = getenv("EKP_CONNECT_FROM_MAT") && atoi(getenv("EKP_CONNECT_FROM_MAT")) != 0;
         if (a.paf_mat && from_mat) { src.ptr = a.paf_mat; src.mode = PAF_FULL_HWC; }
