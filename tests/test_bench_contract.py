@@ -40,3 +40,21 @@ def test_product_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_committed_ncu_figures_belong_to_the_committed_kernels():
+    """profiles/kernels.json (DRAM traffic of the roofline kernel, warp instructions of the issue-bound ones: what the bench
+    line quotes) carries the hash of each kernel source at capture time; bench.py refuses a stale entry at run time, and
+    this test keeps the committed table and the committed sources together: a kernel edit needs a new capture
+    (tools/run_cfg.py under ncu, tools/make_kernels_json.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ekp_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    table = bench.ncu_constants()
+    assert len(table) >= 20
+    stale = sorted(k for k, v in table.items() if v["stale"])
+    assert not stale, f"captured from other sources: {stale}"
+    mat = table["dense_frontend_kernel<mat>|368x432x64|dense_mat"]
+    algo = bench.algo_bytes(46, 54) * 64
+    assert 0.9 * algo <= mat["dram_bytes_per_launch"] <= 1.1 * algo   # no wasted traffic, nothing uncounted
